@@ -1,0 +1,464 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- torch-op restatement of the reference path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package never does.
+
+What is restated, op for op, from the reference (paths relative to /root/reference):
+
+  a1  inlet concentration        SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:45-55
+  a2  MLP forward                ...Eoff_single_model.py:192-208, ...Eon_single_model.py:94-128
+  a3  input scaling              ...Eoff_single_model.py:282-300, ...Eon_single_model.py:243-255
+  a4  output un-scaling / grids  ...Eoff_single_model.py:305-308, ...Eon_single_model.py:257-273
+  a5  enforce_strict             ...Eoff_single_model.py:210-217, ...Eon_single_model.py:69-74
+  a6  linear_interpolation       ...Eoff_single_model.py:106-115
+  a7  CRNNFunc.forward           ...Eoff_single_model.py:135-153, ...Eon_single_model.py:142-151
+  a8  odeint(method='dopri5')    call sites ...Eoff_single_model.py:185, ...Eon_single_model.py:154-155
+  a9  predict_n_ode/crnn_predict ...Eoff_single_model.py:175-186, ...Eon_single_model.py:153-156
+  a10 Eon trim (idx_cut)         ...Eon_single_model.py:346-354
+  a13 ParameterConverter         SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py:194-228
+  a14 loss_n_ode                 ...WIDE_Eoff_surrogate_model_training.py:387-396
+
+PARITY UNPINNED (to the bit) for a8: the integration arithmetic lives in the un-vendored third-party
+package `torchdiffeq` (PyPI, version not pinned by the reference; 0.2.x by its environment), which is
+not installable here (no network) and for which the reference holds no tests or golden vectors.  The
+adaptive dopri5 below restates torchdiffeq 0.2.x's published algorithm
+(`_impl/rk_common.py`, `_impl/dopri5.py`, `_impl/misc.py`, `_impl/interp.py`): same tableau, same
+mixed precision (time in float64, state / tableau / stage times in the state dtype), Hairer initial
+step with order-1, RMS error ratio, step factor clip(0.9*ratio^(-1/5), 0.2|1, 10), FSAL, stages with
+alpha == 1 evaluated at nextafter(t1, -inf), no clipping at output times, quartic dense output.
+Everything else (a1-a7, a9-a14) is pinned by the reference's own artefacts: the
+updated_p -> final_parameters known-answer pairs in two .npz histories and the structural invariants
+of all eight (tests/test_oracle_pins.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+# ---------------------------------------------------------------------------------------------
+# constants (…Eon_single_model.py:56-64, …Eoff_single_model.py:39-40,123-129)
+# ---------------------------------------------------------------------------------------------
+NS, NR, NTOTAL = 9, 9, 801
+LB, UB = 1.0e-6, 6.0e1
+INTER_MIN, INTER_MAX = -3.0e1, 3.0e1
+R_KCAL = 1.9872036e-3
+LL_DU, UL_DU = -1.0e5, 1.0e5
+STEAM_DILUTION_RATIO = 0.7
+R_J = 8.314462618
+# Cantera 3.0 atomic weights (DETAILED_KINETIC_MODEL/LLNL.yaml:19): C 12.011, H 1.008, O 15.999
+MW_NC6H14 = 6 * 12.011 + 14 * 1.008
+MW_H2O = 2 * 1.008 + 15.999
+TIME_IN_LO = np.array([870.0, 1.0e5, 0.5, 2.5])
+TIME_IN_HI = np.array([1150.0, 3.0e5, 1.0, 5.0])
+FULL_L, FULL_U0 = 1.0, 2.5  # …Eon_single_model.py:309
+
+
+# ---------------------------------------------------------------------------------------------
+# a1
+# ---------------------------------------------------------------------------------------------
+def inlet_concentration(T: np.ndarray, P: np.ndarray) -> np.ndarray:
+    """c0[N,9] float32; only column ns-3 non-zero.  T, P float32 arrays (P in Pa).
+
+    numpy-2 (NEP 50) semantics of `(P_ini / (R_J * T_ini)) * (1 / (0.7 * (mw_hex / mw_h2o) + 1))`
+    with np.float32 P_ini/T_ini, python-float R_J and np.float64 molecular weights: the quotient is
+    float32, the product with the float64 factor is float64, the store rounds to float32.
+    """
+    T = np.asarray(T, dtype=np.float32)
+    P = np.asarray(P, dtype=np.float32)
+    factor = np.float64(1.0) / (np.float64(STEAM_DILUTION_RATIO) * (np.float64(MW_NC6H14) / np.float64(MW_H2O)) + 1)
+    q = P / (np.float32(R_J) * T)  # float32
+    c = (q.astype(np.float64) * factor).astype(np.float32)
+    out = np.zeros((T.shape[0], NS), dtype=np.float32)
+    out[:, NS - 3] = c
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a2-a5: MLPs and grids
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class MLPParams:
+    """fc{1..4}.{weight,bias} float32 (nn.Linear layout [out,in]) + the .pkl output scaler."""
+    w: list  # 4 arrays [out,in]
+    b: list  # 4 arrays [out]
+    out_min: float
+    out_max: float
+
+    @property
+    def in_dim(self):
+        return self.w[0].shape[1]
+
+
+def mlp_forward(p: MLPParams, x: np.ndarray, dtype=torch.float32) -> np.ndarray:
+    """fc4(relu(fc3(relu(fc2(relu(fc1(x))))))) with torch CPU kernels (the reference's arithmetic)."""
+    with torch.no_grad():
+        h = torch.as_tensor(np.asarray(x), dtype=dtype)
+        for i in range(4):
+            h = torch.nn.functional.linear(h, torch.as_tensor(p.w[i], dtype=dtype), torch.as_tensor(p.b[i], dtype=dtype))
+            if i < 3:
+                h = torch.relu(h)
+    return h.numpy()
+
+
+def scale_inputs(cols, in_dim: int) -> np.ndarray:
+    """x[N,in_dim] float32 = (v - lo) / (hi - lo) in float32 tensor arithmetic (…Eoff…:296-300)."""
+    n = len(cols[0])
+    x = torch.zeros((n, in_dim), dtype=torch.float32)
+    for k in range(in_dim):
+        v = torch.as_tensor(np.asarray(cols[k], dtype=np.float32))
+        x[:, k] = (v - float(TIME_IN_LO[k])) / float(TIME_IN_HI[k] - TIME_IN_LO[k])
+    return x.numpy()
+
+
+def unscale(out_s: np.ndarray, out_min: float, out_max: float) -> np.ndarray:
+    """out_s * (max - min) + min, float32 tensor times python-scalar semantics (…Eoff…:305)."""
+    t = torch.as_tensor(out_s, dtype=torch.float32)
+    return (t * (np.float64(out_max) - np.float64(out_min)) + np.float64(out_min)).numpy()
+
+
+def enforce_strict(arr: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """In-place sequential repair on a float32 row (…Eon…:69-74)."""
+    assert arr.dtype == np.float32
+    e = np.float32(eps)
+    for i in range(1, len(arr)):
+        if arr[i] <= arr[i - 1]:
+            arr[i] = arr[i - 1] + e
+    return arr
+
+
+def time_grid(p: MLPParams, T, P, L, u0, dtype=torch.float32) -> np.ndarray:
+    """tgrid[N,801] float32 = enforce_strict([0, unscale(mlp(scale(T,P,L,u0)))])."""
+    x = scale_inputs([T, P, L, u0], 4)
+    o = unscale(mlp_forward(p, x, dtype).astype(np.float32), p.out_min, p.out_max)
+    g = np.concatenate([np.zeros((o.shape[0], 1), np.float32), o], axis=1)
+    for i in range(g.shape[0]):
+        enforce_strict(g[i])
+    return g
+
+
+def temp_profile(p: MLPParams, T, P, dtype=torch.float32) -> np.ndarray:
+    """Tprof[N,801] float32 = [T0, unscale(mlp(scale(T,P)))] (…Eon…:257-263)."""
+    x = scale_inputs([T, P], 2)
+    o = unscale(mlp_forward(p, x, dtype).astype(np.float32), p.out_min, p.out_max)
+    return np.concatenate([np.asarray(T, np.float32)[:, None], o], axis=1)
+
+
+def eon_idx_cut(t_full: np.ndarray, t_end: float) -> int:
+    """argmin |t_full - end_time| in float32, first minimum (…Eon…:348-350)."""
+    return int(np.argmin(np.abs(t_full.astype(np.float32) - np.float32(t_end))))
+
+
+# ---------------------------------------------------------------------------------------------
+# a6, a7: right-hand side
+# ---------------------------------------------------------------------------------------------
+def linear_interpolation(tsteps: torch.Tensor, values: torch.Tensor):
+    def interpolate(t):
+        indices = torch.searchsorted(tsteps, t, right=True).clamp(1, len(tsteps) - 1)
+        x0 = tsteps[indices - 1]
+        x1 = tsteps[indices]
+        y0 = values[indices - 1]
+        y1 = values[indices]
+        slope = (y1 - y0) / (x1 - x0)
+        return y0 + slope * (t - x0)
+    return interpolate
+
+
+class CRNNFunc:
+    """f(t,u) of the reference; dtype follows u.  Clamp values are overridable for the training RHS
+    (WIDE_Eoff…:39-43 uses +-10)."""
+
+    def __init__(self, t_ar, T_ar, w_in, w_b, w_out, inter=(INTER_MIN, INTER_MAX), lb=LB, ub=UB):
+        self.itpT = linear_interpolation(t_ar, T_ar)
+        self.w_in, self.w_b, self.w_out = w_in, w_b, w_out
+        self.inter = inter
+        self.lb, self.ub = lb, ub
+        self.nfe = 0
+
+    def __call__(self, t, u):
+        self.nfe += 1
+        dt = u.dtype
+        Tq = self.itpT(t)
+        Y = torch.clamp(u, self.lb, self.ub)
+        logX = torch.log(Y)
+        R = torch.tensor(R_KCAL, dtype=dt)
+        w_v = torch.cat([logX, torch.stack([-1 / (R * Tq), torch.log(Tq)]).to(dt)])
+        inter = torch.matmul(self.w_in.T, w_v) + self.w_b
+        inter = torch.clamp(inter, self.inter[0], self.inter[1])
+        du = torch.matmul(self.w_out, torch.exp(inter))
+        return torch.clamp(du, LL_DU, UL_DU)
+
+
+def crnn_rhs_np(T, u, w_in, w_b, w_out, dtype=np.float64, inter=(INTER_MIN, INTER_MAX)):
+    """Batched numpy RHS at given temperatures: T[N], u[N,9] -> du[N,9] (a7 without the lookup)."""
+    T = np.asarray(T, dtype)
+    u = np.asarray(u, dtype)
+    w_in = np.asarray(w_in, dtype)
+    Y = np.clip(u, dtype(LB), dtype(UB))
+    wv = np.concatenate([np.log(Y), (-1 / (dtype(R_KCAL) * T))[:, None], np.log(T)[:, None]], axis=1)
+    z = np.clip(wv @ w_in + np.asarray(w_b, dtype), dtype(inter[0]), dtype(inter[1]))
+    du = np.exp(z) @ np.asarray(w_out, dtype).T
+    return np.clip(du, dtype(LL_DU), dtype(UL_DU))
+
+
+# ---------------------------------------------------------------------------------------------
+# a8: torchdiffeq-semantics dopri5
+# ---------------------------------------------------------------------------------------------
+_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_C_SOL = [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0]
+_C_ERR = [
+    35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+    -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0,
+]
+_C_MID = [
+    6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+    187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2,
+]
+
+
+def _rms(x):
+    return x.abs().pow(2).mean().sqrt()
+
+
+@dataclass
+class SolveStats:
+    nfe: int = 0
+    accepted: int = 0
+    rejected: int = 0
+
+
+def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6, stats: SolveStats | None = None,
+                  max_num_steps=2 ** 31 - 1):
+    """torchdiffeq.odeint(func, y0, t, method='dopri5') restated (see module header).  Returns [len(t), 9]."""
+    sd = y0.dtype
+    alpha = [torch.tensor(a, dtype=sd) for a in _ALPHA]
+    beta = [torch.tensor(b, dtype=sd) for b in _BETA]
+    c_err = torch.tensor(_C_ERR, dtype=sd)
+    c_mid = torch.tensor(_C_MID, dtype=sd)
+    if not bool((t[1:] > t[:-1]).all()):
+        raise ValueError("t must be strictly increasing or decreasing")
+    t = t.to(torch.float64)
+    stats = stats if stats is not None else SolveStats()
+
+    def f(tt, y, prev=False):
+        tt = tt.to(sd)
+        if prev:
+            tt = torch.nextafter(tt, tt - 1)
+        stats.nfe += 1
+        return func(tt, y)
+
+    # _before_integrate + _select_initial_step(order = 5 - 1)
+    f0 = f(t[0], y0)
+    scale = atol + torch.abs(y0) * rtol
+    d0 = _rms(y0 / scale)
+    d1 = _rms(f0 / scale)
+    if d0 < 1e-5 or d1 < 1e-5:
+        h0 = torch.tensor(1e-6, dtype=sd)
+    else:
+        h0 = 0.01 * d0 / d1
+    h0 = h0.abs()
+    y1 = y0 + h0 * f0
+    f1 = f(t[0] + h0, y1)
+    d2 = torch.abs(_rms((f1 - f0) / scale) / h0)
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = torch.max(torch.tensor(1e-6, dtype=sd), h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    h1 = h1.abs()
+    dt = torch.min(100 * h0, h1).to(torch.float64)
+
+    rk_y, rk_f, rk_t0, rk_t1 = y0, f0, t[0], t[0]
+    interp = [y0] * 5
+    sol = torch.empty(len(t), *y0.shape, dtype=sd)
+    sol[0] = y0
+    for i in range(1, len(t)):
+        next_t = t[i]
+        n_steps = 0
+        while next_t > rk_t1:
+            assert n_steps < max_num_steps
+            # ---- _adaptive_step ----
+            ya, fa, ta = rk_y, rk_f, rk_t1
+            tb = ta + dt
+            assert ta + dt > ta, "underflow in dt"
+            assert torch.isfinite(ya).all(), "non-finite values in state `y`"
+            # ---- _runge_kutta_step ----
+            t0s, dts, t1s = ta.to(sd), dt.to(sd), tb.to(sd)
+            k = torch.empty(*fa.shape, 7, dtype=sd)
+            k[..., 0] = fa
+            for j, (al, be) in enumerate(zip(alpha, beta)):
+                if float(al) == 1.0:
+                    ti, prev = t1s, True
+                else:
+                    ti, prev = t0s + al * dts, False
+                yi = ya + torch.sum(k[..., : j + 1] * (be * dts), dim=-1).view_as(fa)
+                k[..., j + 1] = f(ti, yi, prev)
+            yb = yi
+            fb = k[..., -1]
+            err = torch.sum(k * (dts * c_err), dim=-1)
+            tol = atol + rtol * torch.max(ya.abs(), yb.abs())
+            ratio = _rms(err / tol).abs()
+            accept = bool(ratio <= 1)
+            if accept:
+                dtt = dt.to(sd)
+                y_mid = ya + k.matmul(dtt * c_mid).view_as(ya)
+                fa0 = k[..., 0]
+                a = 2 * dtt * (fb - fa0) - 8 * (yb + ya) + 16 * y_mid
+                b = dtt * (5 * fa0 - 3 * fb) + 18 * ya + 14 * yb - 32 * y_mid
+                c = dtt * (fb - 4 * fa0) - 11 * ya - 5 * yb + 16 * y_mid
+                d = dtt * fa0
+                interp = [ya, d, c, b, a]
+                rk_y, rk_f, rk_t0, rk_t1 = yb, fb, ta, tb
+                stats.accepted += 1
+            else:
+                rk_t0 = ta
+                stats.rejected += 1
+            # ---- _optimal_step_size ----
+            if ratio == 0:
+                dt = dt * 10.0
+            else:
+                dfac = 1.0 if ratio < 1 else 0.2
+                r64 = ratio.to(torch.float64)
+                factor = torch.min(torch.tensor(10.0, dtype=torch.float64),
+                                   torch.max(0.9 / r64 ** torch.tensor(5.0, dtype=torch.float64).reciprocal(),
+                                             torch.tensor(dfac, dtype=torch.float64)))
+                dt = dt * factor
+            n_steps += 1
+        # ---- _interp_evaluate ----
+        x = ((next_t - rk_t0) / (rk_t1 - rk_t0)).to(sd)
+        total = interp[0] + x * interp[1]
+        xp = x
+        for coef in interp[2:]:
+            xp = xp * x
+            total = total + xp * coef
+        sol[i] = total
+    return sol
+
+
+# ---------------------------------------------------------------------------------------------
+# a9, a10
+# ---------------------------------------------------------------------------------------------
+def crnn_predict(t_ar, T_ar, u0, w_in, w_b, w_out, rtol=1e-6, atol=1e-6, dtype=torch.float32,
+                 inter=(INTER_MIN, INTER_MAX), stats: SolveStats | None = None) -> np.ndarray:
+    """clamp(odeint(CRNNFunc, u0, t_ar, dopri5).T, lb, ub) -> [9,801] (…Eon…:153-156; predict_n_ode …Eoff…:175-186)."""
+    tt = torch.as_tensor(np.asarray(t_ar), dtype=dtype)
+    TT = torch.as_tensor(np.asarray(T_ar), dtype=dtype)
+    f = CRNNFunc(tt, TT, torch.as_tensor(w_in, dtype=dtype), torch.as_tensor(w_b, dtype=dtype),
+                 torch.as_tensor(w_out, dtype=dtype), inter=inter)
+    sol = odeint_dopri5(f, torch.as_tensor(np.asarray(u0), dtype=dtype), tt, rtol=rtol, atol=atol, stats=stats)
+    return torch.clamp(sol.T, LB, UB).numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# converged truth: knot-to-knot DOP853 in float64 (RHS is smooth inside each knot interval)
+# ---------------------------------------------------------------------------------------------
+def converged_trajectory(t_ar, T_ar, u0, w_in, w_b, w_out, upto: int | None = None, rtol=1e-12, atol=1e-14,
+                         inter=(INTER_MIN, INTER_MAX)) -> np.ndarray:
+    """y[upto+1, 9] float64 at the knots t_ar[0..upto]; T(t) piecewise linear in float64 between knots."""
+    from scipy.integrate import solve_ivp
+
+    t = np.asarray(t_ar, np.float64)
+    Tk = np.asarray(T_ar, np.float64)
+    w_in = np.asarray(w_in, np.float64)
+    w_b = np.asarray(w_b, np.float64)
+    w_out = np.asarray(w_out, np.float64)
+    upto = len(t) - 1 if upto is None else upto
+    y = np.asarray(u0, np.float64).copy()
+    out = np.empty((upto + 1, NS))
+    out[0] = y
+    for i in range(upto):
+        slope = (Tk[i + 1] - Tk[i]) / (t[i + 1] - t[i])
+
+        def rhs(tt, yy, i=i, slope=slope):
+            Tq = Tk[i] + slope * (tt - t[i])
+            Y = np.clip(yy, LB, UB)
+            wv = np.concatenate([np.log(Y), [-1 / (R_KCAL * Tq), math.log(Tq)]])
+            z = np.clip(w_in.T @ wv + w_b, inter[0], inter[1])
+            return np.clip(w_out @ np.exp(z), LL_DU, UL_DU)
+
+        s = solve_ivp(rhs, (t[i], t[i + 1]), y, method="DOP853", rtol=rtol, atol=atol)
+        assert s.success
+        y = s.y[:, -1]
+        out[i + 1] = y
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a13, a14 (training)
+# ---------------------------------------------------------------------------------------------
+E_H = [2, 4, 4, 6, 6, 8, 14, 10, 10]
+E_C = [0, 1, 2, 2, 3, 4, 6, 4, 5]
+
+
+def element_nullspace(dtype=torch.float32) -> torch.Tensor:
+    """E_null [9,7] (WIDE_Eoff…:129-133)."""
+    E_ = torch.stack([torch.tensor(E_H, dtype=dtype), torch.tensor(E_C, dtype=dtype)], dim=1)
+    _, _, Vh = torch.linalg.svd(E_.T, full_matrices=True)
+    return Vh[E_.size(1):].T
+
+
+@dataclass
+class ConverterSpec:
+    """Which trainer's ParameterConverter: fits, clamps and slope formulas.
+
+    wide : WIDE_Eoff_surrogate_model_training.py:25-29,48-52,186-188
+    eoff : Eoff_surrogate_model_training.py (narrow clamps, same slope form with its own fits)
+    eon  : Eon_surrogate_model_training.py:287-327
+    """
+    A_fit: float = 18.42068
+    b_fit: float = 2.112
+    Ea_fit: float = 63.304
+    slope_reg: float = 0.5
+    wout: tuple = (-5.0, 5.0)
+    win: tuple = (0.0, 5.0)
+    Ea: tuple = (5.0, 200.0)
+    b: tuple = (-3.0, 3.0)
+    A: tuple = (1.0, 21.0)
+
+
+def converter_slopes(spec: ConverterSpec):
+    f32 = torch.float32
+    A, b, Ea, reg = (torch.tensor(v, dtype=f32) for v in (spec.A_fit, spec.b_fit, spec.Ea_fit, spec.slope_reg))
+    slope_A = A * (A / (A + NR)) * reg
+    slope_b = b * ((A + b + NR) / (A + b + NR + NS)) * reg
+    slope_Ea = Ea * ((Ea + A + NR) / (Ea - NR)) * reg
+    return slope_A, slope_b, slope_Ea
+
+
+def parameter_converter(p: torch.Tensor, spec: ConverterSpec = ConverterSpec(), E_null: torch.Tensor | None = None):
+    """p[189] -> (w_in[11,9], w_b[9], w_out[9,9]), differentiable (WIDE_Eoff…:194-228)."""
+    E_null = element_nullspace() if E_null is None else E_null
+    slope_A, slope_b, slope_Ea = converter_slopes(spec)
+    w_b = torch.abs(p[:NR]) * slope_A
+    w_in_b = p[NR:NR * 2] * slope_b
+    w_in_Ea = torch.abs(p[NR * 2:NR * 3] * slope_Ea)
+    w_out = p[NR * 3:NR * (NS + 3)].view(NS, NR)
+    w_adj = w_out.clone()
+    eye = torch.eye(E_null.shape[1], dtype=torch.float32)
+    cols = []
+    for i in range(NR):
+        abcd = torch.linalg.solve(E_null.T @ E_null + 1e-4 * eye, E_null.T @ w_adj[:, i]).to(torch.float32)
+        cols.append(E_null @ abcd)
+    w_adj = torch.stack(cols, dim=1)
+    w_adj = torch.clamp(w_adj, spec.wout[0], spec.wout[1])
+    w_in_only = torch.clamp(-w_adj, spec.win[0], spec.win[1])
+    w_in_Ea = torch.clamp(w_in_Ea, spec.Ea[0], spec.Ea[1])
+    w_in_b = torch.clamp(w_in_b, spec.b[0], spec.b[1])
+    w_b = torch.clamp(w_b, spec.A[0], spec.A[1])
+    w_in = torch.cat([w_in_only, w_in_Ea.unsqueeze(0), w_in_b.unsqueeze(0)], dim=0)
+    return w_in, w_b, w_adj
+
+
+def loss_n_ode(pred: torch.Tensor, ref: torch.Tensor, yscale: torch.Tensor) -> torch.Tensor:
+    """mse(pred[0:7]/yscale, ref[0:7]/yscale) (WIDE_Eoff…:387-396). pred/ref [9,801], yscale [9]."""
+    s = yscale[:7].unsqueeze(1)
+    return torch.nn.functional.mse_loss(pred[:7] / s, ref[:7] / s)
