@@ -1,0 +1,107 @@
+/* crnn_pfr.h -- C ABI of the B200-native batched CRNN plug-flow-reactor surrogate.
+ *
+ * The reference (CHOIHSpotato/n-hexane-pyrolysis-surrogate-reactor-model) has no FFI: its surrogate path
+ * is a set of Python call seams.  Each entry point below names the seam it replaces (paths relative to
+ * the reference checkout).  Conventions:
+ *   - every data pointer is DEVICE memory owned by the caller; the library allocates only what its own
+ *     handles hold (uploaded parameters); nothing here synchronises the device unless stated;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *   - per-condition arrays are SoA with the condition index fastest: x[n], grid[801][n], y[9][n];
+ *   - return value: PFR_OK or a negative PFR_E* code; per-condition solver outcomes go to status[n].
+ * One host thread per GPU; handles are bound to the device current at creation.
+ */
+#ifndef CRNN_PFR_H
+#define CRNN_PFR_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFR_OK 0
+#define PFR_EINVAL (-1)     /* bad argument */
+#define PFR_ECUDA (-2)      /* CUDA runtime error (pfr_last_cuda_error() has the text) */
+#define PFR_EWORKSPACE (-3) /* workspace too small */
+
+#define PFR_NS 9      /* species: H2 CH4 C2H4 C2H6 C3H6 C4H8-1 NC6H14 C4H10 C5H10-1 */
+#define PFR_NR 9      /* pseudo-reactions */
+#define PFR_NKNOTS 801
+
+/* per-condition solver status (mirrors torchdiffeq's asserts) */
+#define PFR_ST_OK 0
+#define PFR_ST_MAXSTEPS 1
+#define PFR_ST_NONFINITE 2
+#define PFR_ST_UNDERFLOW 3
+
+#define PFR_METHOD_RODAS4 0 /* adaptive Rosenbrock, knot-aware (the product integrator) */
+#define PFR_METHOD_DOPRI5 1 /* torchdiffeq-semantics dopri5 (reference-behaviour mode) */
+
+typedef struct crnn_model* crnn_model_t;
+typedef struct pfr_mlp* pfr_mlp_t;
+
+int pfr_version(void);
+const char* pfr_status_string(int code);
+const char* pfr_last_cuda_error(void);
+
+/* CRNN parameters: `parameters[-1]` of a training history
+ *   load_npz_parameters                      SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:223-230
+ * w_in[11][9] (rows 0-8 reaction orders, 9 Ea [kcal/mol], 10 b), w_b[9] = ln A, w_out[9][9], HOST pointers.
+ * clamps = {lb, ub, zlo, zhi, dulo, duhi} or NULL for the inference defaults {1e-6, 60, -30, 30, -1e5, 1e5}
+ *   (...Eoff_single_model.py:123-129; the WIDE trainer uses zlo/zhi = -/+10). */
+int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out);
+int crnn_model_destroy(crnn_model_t m);
+
+/* 512-wide predictor MLP (nn.Linear layout [out][in], HOST pointers) + its .pkl output scaler
+ *   MultiLayerPerceptron_time / MLP_Time / MLP_Temp   ...Eoff_single_model.py:192-208, ...Eon_single_model.py:94-128
+ * in_dim 4: (T, P, L, u0) time predictor; in_dim 2: (T, P) temperature predictor.
+ * in_lo/in_hi [in_dim]: input scaling bounds (...Eoff_single_model.py:282-283). */
+int pfr_mlp_create(int in_dim, const float* const weights[4], const float* const biases[4], double out_min,
+                   double out_max, const double* in_lo, const double* in_hi, pfr_mlp_t* out);
+int pfr_mlp_destroy(pfr_mlp_t mlp);
+/* scratch needed by the calls below for batches processed `chunk` conditions at a time (chunk<=0: default) */
+size_t pfr_mlp_workspace_bytes(int n, int chunk);
+
+/* calculate_spec_conc_0_list / build_spec_conc_0_list   ...Eoff_single_model.py:45-55, ...Eon_single_model.py:41-50
+ * c0[n]: inlet n-hexane concentration (mol/m3); P in Pa. */
+int pfr_inlet_concentration(const float* T, const float* P, int n, float* c0, void* stream);
+
+/* model_time(x) -> un-scale -> cat(t0, .) -> enforce_strict   ...Eoff_single_model.py:296-318
+ * predict_time_profile(T,P,L,u)                                ...Eon_single_model.py:265-273
+ * L/u0 NULL: the full-length grid at L = 1.0 m, u0 = 2.5 m/s (...Eon_single_model.py:309).
+ * tgrid [801][n] and/or t_end [n] (= tgrid[800]); either may be NULL.
+ * raw != 0: skip un-scaling and enforce_strict, rows 1..800 receive the bare network output (row 0 = 0). */
+int pfr_time_grid(pfr_mlp_t mlp, const float* T, const float* P, const float* L, const float* u0, int n, float* tgrid,
+                  float* t_end, int raw, void* workspace, size_t workspace_bytes, int chunk, void* stream);
+
+/* predict_temp_profile(T,P) = [T0, mlp*(max-min)+min]   ...Eon_single_model.py:257-263 ; Tprof [801][n] */
+int pfr_temp_profile(pfr_mlp_t mlp, const float* T, const float* P, int n, float* Tprof, int raw, void* workspace,
+                     size_t workspace_bytes, int chunk, void* stream);
+
+/* idx_cut = argmin |t_full - end_time|   ...Eon_single_model.py:348-350 ; idx [n] */
+int pfr_idx_cut(const float* t_full, const float* t_end, int n, int* idx, void* stream);
+
+/* CRNNFunc.forward at given temperatures (first-kernel parity hook)   ...Eoff_single_model.py:135-153
+ * precision 64: T[n], u[9][n], du[9][n] double; precision 32: float. */
+int pfr_rhs(crnn_model_t m, int n, const void* T, const void* u, void* du, int precision, void* stream);
+
+/* Trainer.predict_n_ode / crnn_predict = clamp(odeint(CRNNFunc, u0, t, ...))   ...Eoff_single_model.py:175-186,
+ *                                                                             ...Eon_single_model.py:153-156
+ * T0[n], c0[n]; tgrid[801][n] or NULL (then t_end[n] gives the final time and Tprof must be NULL);
+ * Tprof[801][n] or NULL (isothermal, T = T0); idx_end[n] or NULL (= 800): knot whose state is the outlet.
+ * y_out[9][n] (double for precision 64, float for 32), clamped to [lb, ub]; y_dense[801][9][n] or NULL
+ * (requires tgrid); status[n]; stats[3][n] = accepted steps, rejected steps, RHS evaluations (or NULL).
+ * perm[n] or NULL: thread j integrates condition perm[j] -- a cost-sorted order keeps the lanes of a warp in
+ * step with each other; every array is still indexed by the condition, so outputs need no un-permuting. */
+int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
+                  const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
+                  double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats,
+                  void* stream);
+
+/* Pipe micro-benchmarks used as roofline denominators (synchronous; a few ms each).
+ * out[0] FP32 FFMA flop/s, out[1] FP64 DFMA flop/s, out[2] MUFU.EX2 op/s, out[3] SM clock seen (Hz, from clock64). */
+int pfr_measure_peaks(double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRNN_PFR_H */

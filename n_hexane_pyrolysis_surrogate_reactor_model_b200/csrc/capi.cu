@@ -1,0 +1,422 @@
+// C-ABI entry points (include/crnn_pfr.h): handle management, argument checks, kernel launches.
+#include "../../include/crnn_pfr.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "crnn_device.cuh"
+#include "integrate_dopri5.cuh"
+#include "integrate_rodas.cuh"
+#include "mlp.cuh"
+
+using namespace pfr;
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return PFR_ECUDA;
+}
+#define CK(call)                                             \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+    } while (0)
+#define CK_LAUNCH(name)                                        \
+    do {                                                       \
+        cudaError_t e_ = cudaGetLastError();                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, name);     \
+    } while (0)
+
+struct crnn_model {
+    CrnnParams<double> pd;
+    CrnnParams<float> pf;
+};
+
+struct pfr_mlp {
+    int in_dim;
+    int npad4;  // output layer padded to a multiple of GEMM_BM
+    float *W1, *b1, *Wt2, *b2, *Wt3, *b3, *Wt4, *b4;
+    float span, omin;
+    MlpInputScale sc;
+};
+
+constexpr int DEFAULT_CHUNK = 65536;
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int eff_chunk(int n, int chunk) {
+    if (chunk <= 0) chunk = DEFAULT_CHUNK;
+    chunk = round_up(chunk, GEMM_BN);
+    const int nn = round_up(n < 1 ? 1 : n, GEMM_BN);
+    return chunk < nn ? chunk : nn;
+}
+
+extern "C" int pfr_version(void) { return 100; }
+
+extern "C" const char* pfr_status_string(int code) {
+    switch (code) {
+        case PFR_OK: return "ok";
+        case PFR_EINVAL: return "invalid argument";
+        case PFR_ECUDA: return "CUDA error";
+        case PFR_EWORKSPACE: return "workspace too small";
+        default: return "unknown";
+    }
+}
+extern "C" const char* pfr_last_cuda_error(void) { return g_cuda_err; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out) {
+    if (!w_in || !w_b || !w_out || !out) return PFR_EINVAL;
+    crnn_model* m = new (std::nothrow) crnn_model;
+    if (!m) return PFR_EINVAL;
+    const double def[6] = {1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5};
+    const double* c = clamps ? clamps : def;
+    // the reference holds R_kcal as a float32 tensor / rounds it to float32 in the multiply
+    const float Rk = 1.9872036e-3f;
+    for (int k = 0; k < NS; k++)
+        for (int j = 0; j < NR; j++) {
+            m->pd.nu[k][j] = (double)w_in[k * NR + j];
+            m->pf.nu[k][j] = w_in[k * NR + j];
+            m->pd.wout[k][j] = (double)w_out[k * NR + j];
+            m->pf.wout[k][j] = w_out[k * NR + j];
+        }
+    for (int j = 0; j < NR; j++) {
+        m->pd.Ea[j] = (double)w_in[9 * NR + j];
+        m->pf.Ea[j] = w_in[9 * NR + j];
+        m->pd.b[j] = (double)w_in[10 * NR + j];
+        m->pf.b[j] = w_in[10 * NR + j];
+        m->pd.lnA[j] = (double)w_b[j];
+        m->pf.lnA[j] = w_b[j];
+    }
+    m->pd.lb = c[0]; m->pd.ub = c[1]; m->pd.zlo = c[2]; m->pd.zhi = c[3]; m->pd.dulo = c[4]; m->pd.duhi = c[5];
+    m->pf.lb = (float)c[0]; m->pf.ub = (float)c[1]; m->pf.zlo = (float)c[2]; m->pf.zhi = (float)c[3];
+    m->pf.dulo = (float)c[4]; m->pf.duhi = (float)c[5];
+    m->pd.inv_R = 1.0 / (double)Rk;
+    m->pf.inv_R = 1.0f / Rk;
+    *out = m;
+    return PFR_OK;
+}
+
+extern "C" int crnn_model_destroy(crnn_model_t m) {
+    delete m;
+    return PFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int upload(const std::vector<float>& h, float** d) {
+    CK(cudaMalloc((void**)d, h.size() * sizeof(float)));
+    CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const float* const biases[4], double out_min,
+                   double out_max, const double* in_lo, const double* in_hi, pfr_mlp_t* out) {
+    if ((in_dim != 2 && in_dim != 4) || !weights || !biases || !in_lo || !in_hi || !out) return PFR_EINVAL;
+    for (int i = 0; i < 4; i++)
+        if (!weights[i] || !biases[i]) return PFR_EINVAL;
+    pfr_mlp* m = new (std::nothrow) pfr_mlp;
+    if (!m) return PFR_EINVAL;
+    memset(m, 0, sizeof(*m));
+    m->in_dim = in_dim;
+    m->npad4 = round_up(MLP_OUT, GEMM_BM);
+    // `out * (max - min) + min`: (max - min) in double, both scalars rounded to float32 by the tensor op
+    m->span = (float)(out_max - out_min);
+    m->omin = (float)out_min;
+    for (int k = 0; k < 4; k++) { m->sc.lo[k] = 0.f; m->sc.span[k] = 1.f; }
+    for (int k = 0; k < in_dim; k++) { m->sc.lo[k] = (float)in_lo[k]; m->sc.span[k] = (float)(in_hi[k] - in_lo[k]); }
+    m->sc.fullL = 1.0f;
+    m->sc.fullU = 2.5f;
+    int rc;
+    std::vector<float> h;
+    h.assign(weights[0], weights[0] + MLP_HID * in_dim);
+    if ((rc = upload(h, &m->W1))) return rc;
+    h.assign(biases[0], biases[0] + MLP_HID);
+    if ((rc = upload(h, &m->b1))) return rc;
+    // hidden layers: Wt[k][o] = W[o][k]
+    float** wt[2] = {&m->Wt2, &m->Wt3};
+    float** bb[2] = {&m->b2, &m->b3};
+    for (int l = 0; l < 2; l++) {
+        h.assign((size_t)MLP_HID * MLP_HID, 0.f);
+        for (int o = 0; o < MLP_HID; o++)
+            for (int k = 0; k < MLP_HID; k++) h[(size_t)k * MLP_HID + o] = weights[l + 1][(size_t)o * MLP_HID + k];
+        if ((rc = upload(h, wt[l]))) return rc;
+        h.assign(biases[l + 1], biases[l + 1] + MLP_HID);
+        if ((rc = upload(h, bb[l]))) return rc;
+    }
+    h.assign((size_t)MLP_HID * m->npad4, 0.f);
+    for (int o = 0; o < MLP_OUT; o++)
+        for (int k = 0; k < MLP_HID; k++) h[(size_t)k * m->npad4 + o] = weights[3][(size_t)o * MLP_HID + k];
+    if ((rc = upload(h, &m->Wt4))) return rc;
+    h.assign(m->npad4, 0.f);
+    for (int o = 0; o < MLP_OUT; o++) h[o] = biases[3][o];
+    if ((rc = upload(h, &m->b4))) return rc;
+    *out = m;
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_destroy(pfr_mlp_t m) {
+    if (!m) return PFR_OK;
+    float* ptrs[8] = {m->W1, m->b1, m->Wt2, m->b2, m->Wt3, m->b3, m->Wt4, m->b4};
+    for (float* p : ptrs)
+        if (p) cudaFree(p);
+    delete m;
+    return PFR_OK;
+}
+
+extern "C" size_t pfr_mlp_workspace_bytes(int n, int chunk) {
+    const size_t ld = (size_t)eff_chunk(n, chunk);
+    // two activation buffers [512][ld] + one output scratch [800][ld] (t_end-only mode)
+    return (2 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float);
+}
+
+extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, float* c0, void* stream) {
+    if (!T || !P || !c0 || n < 0) return PFR_EINVAL;
+    if (n == 0) return PFR_OK;
+    const double mw_hex = 6 * 12.011 + 14 * 1.008, mw_h2o = 2 * 1.008 + 15.999;  // Cantera 3.0 atomic weights
+    const double factor = 1.0 / (0.7 * (mw_hex / mw_h2o) + 1);
+    inlet_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, P, n, (float)8.314462618, factor, c0);
+    CK_LAUNCH("inlet_kernel");
+    return PFR_OK;
+}
+
+// Shared driver of pfr_time_grid / pfr_temp_profile: chunks of `ld` conditions through the four layers.
+static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
+                   float* t_end, bool is_time, int raw, void* ws, size_t ws_bytes, int chunk, cudaStream_t st) {
+    if (!m || !T || !P || n < 0 || (!grid && !t_end) || !ws) return PFR_EINVAL;
+    if (n == 0) return PFR_OK;
+    const int ld = eff_chunk(n, chunk);
+    if (ws_bytes < (2 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float)) return PFR_EWORKSPACE;
+    float* H1 = static_cast<float*>(ws);
+    float* H2 = H1 + (size_t)MLP_HID * ld;
+    float* S = H2 + (size_t)MLP_HID * ld;  // [800][ld] scratch for the t_end-only mode
+    const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
+    for (int c0 = 0; c0 < n; c0 += ld) {
+        const int mv = (n - c0) < ld ? (n - c0) : ld;
+        const int ldc = round_up(mv, GEMM_BN);  // columns actually computed for this chunk
+        mlp_layer1_kernel<<<(ldc + 255) / 256, 256, 0, st>>>(m->W1, m->b1, m->in_dim, m->sc, T + c0, P + c0,
+                                                             L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv, ld, H1);
+        CK_LAUNCH("mlp_layer1_kernel");
+        dim3 gh(MLP_HID / GEMM_BM, ldc / GEMM_BN);
+        mlp_gemm_kernel<false><<<gh, GEMM_THREADS, 0, st>>>(m->Wt2, m->b2, H1, MLP_HID, MLP_HID, ld, H2, (size_t)ld,
+                                                            MLP_HID, ldc, 1.f, 0.f);
+        CK_LAUNCH("mlp_gemm_kernel<hidden>");
+        mlp_gemm_kernel<false><<<gh, GEMM_THREADS, 0, st>>>(m->Wt3, m->b3, H2, MLP_HID, MLP_HID, ld, H1, (size_t)ld,
+                                                            MLP_HID, ldc, 1.f, 0.f);
+        CK_LAUNCH("mlp_gemm_kernel<hidden>");
+        dim3 go(m->npad4 / GEMM_BM, ldc / GEMM_BN);
+        float* rows = grid ? grid + (size_t)n + c0 : S;  // row 1 of the [801][n] grid, or the scratch
+        const size_t rows_ld = grid ? (size_t)n : (size_t)ld;
+        mlp_gemm_kernel<true><<<go, GEMM_THREADS, 0, st>>>(m->Wt4, m->b4, H1, MLP_HID, m->npad4, ld, rows, rows_ld,
+                                                           MLP_OUT, mv, span, omin);
+        CK_LAUNCH("mlp_gemm_kernel<final>");
+        if (is_time) {
+            if (!raw) {
+                enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, st>>>(rows, rows_ld, mv, grid ? grid + c0 : nullptr,
+                                                                        t_end ? t_end + c0 : nullptr, grid ? 1 : 0);
+                CK_LAUNCH("enforce_strict_kernel");
+            } else if (grid) {
+                CK(cudaMemsetAsync(grid + c0, 0, (size_t)mv * sizeof(float), st));
+            }
+        } else {
+            copy_row_kernel<<<(mv + 255) / 256, 256, 0, st>>>(T + c0, grid + c0, mv);
+            CK_LAUNCH("copy_row_kernel");
+        }
+    }
+    return PFR_OK;
+}
+
+extern "C" int pfr_time_grid(pfr_mlp_t mlp, const float* T, const float* P, const float* L, const float* u0, int n, float* tgrid,
+                  float* t_end, int raw, void* workspace, size_t workspace_bytes, int chunk, void* stream) {
+    if (!mlp || mlp->in_dim != 4) return PFR_EINVAL;
+    if ((L == nullptr) != (u0 == nullptr)) return PFR_EINVAL;
+    if (raw && !tgrid) return PFR_EINVAL;
+    return mlp_run(mlp, T, P, L, u0, n, tgrid, t_end, true, raw, workspace, workspace_bytes, chunk, (cudaStream_t)stream);
+}
+
+extern "C" int pfr_temp_profile(pfr_mlp_t mlp, const float* T, const float* P, int n, float* Tprof, int raw, void* workspace,
+                     size_t workspace_bytes, int chunk, void* stream) {
+    if (!mlp || mlp->in_dim != 2 || !Tprof) return PFR_EINVAL;
+    return mlp_run(mlp, T, P, nullptr, nullptr, n, Tprof, nullptr, false, raw, workspace, workspace_bytes, chunk,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int pfr_idx_cut(const float* t_full, const float* t_end, int n, int* idx, void* stream) {
+    if (!t_full || !t_end || !idx || n < 0) return PFR_EINVAL;
+    if (n == 0) return PFR_OK;
+    idx_cut_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t_full, (size_t)n, t_end, n, idx);
+    CK_LAUNCH("idx_cut_kernel");
+    return PFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(128)
+rhs_kernel(const __grid_constant__ CrnnParams<real> p, int n, const real* __restrict__ T, const real* __restrict__ u,
+           real* __restrict__ du) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    real kT[NR], dkT[NR], y[NS], f[NS], g[NR], q[NS], md[NS];
+    arrhenius_T<real, false>(p, T[i], kT, dkT);
+#pragma unroll
+    for (int k = 0; k < NS; k++) y[k] = u[(size_t)k * n + i];
+    crnn_rhs<real, false>(p, kT, y, f, g, q, md);
+#pragma unroll
+    for (int k = 0; k < NS; k++) du[(size_t)k * n + i] = f[k];
+}
+
+extern "C" int pfr_rhs(crnn_model_t m, int n, const void* T, const void* u, void* du, int precision, void* stream) {
+    if (!m || !T || !u || !du || n < 0 || (precision != 32 && precision != 64)) return PFR_EINVAL;
+    if (n == 0) return PFR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 64)
+        rhs_kernel<double><<<(n + 127) / 128, 128, 0, st>>>(m->pd, n, (const double*)T, (const double*)u, (double*)du);
+    else
+        rhs_kernel<float><<<(n + 127) / 128, 128, 0, st>>>(m->pf, n, (const float*)T, (const float*)u, (float*)du);
+    CK_LAUNCH("rhs_kernel");
+    return PFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename real, bool kRamp, bool kKnots>
+static int launch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
+    auto kern = rodas4_kernel<real, kRamp, kKnots>;
+    const size_t smem = (size_t)sm_entries<kRamp>() * RODAS_BLOCK * sizeof(real);
+    static bool configured = false;  // per template instantiation
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<(a.n + RODAS_BLOCK - 1) / RODAS_BLOCK, RODAS_BLOCK, smem, st>>>(p, a);
+    CK_LAUNCH("rodas4_kernel");
+    return PFR_OK;
+}
+
+template <typename real>
+static int dispatch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
+    if (a.Tprof) return launch_rodas<real, true, true>(p, a, st);
+    // isothermal: knot-limited only when the knots matter (dense output, or an outlet knot other than the last)
+    if (a.y_dense || a.idx_end) return launch_rodas<real, false, true>(p, a, st);
+    return launch_rodas<real, false, false>(p, a, st);
+}
+
+template <typename real>
+static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaStream_t st) {
+    const int grid = (a.n + DOPRI_BLOCK - 1) / DOPRI_BLOCK;
+    if (a.Tprof) dopri5_kernel<real, true><<<grid, DOPRI_BLOCK, 0, st>>>(p, a);
+    else dopri5_kernel<real, false><<<grid, DOPRI_BLOCK, 0, st>>>(p, a);
+    CK_LAUNCH("dopri5_kernel");
+    return PFR_OK;
+}
+
+extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
+                  const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
+                  double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats, void* stream) {
+    if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
+    if (precision != 32 && precision != 64) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5) return PFR_EINVAL;
+    if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
+    if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
+    if (n == 0) return PFR_OK;
+    if (max_steps <= 0) max_steps = 1000000;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (method == PFR_METHOD_RODAS4) {
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
+        return precision == 64 ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
+    }
+    Dopri5Args a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
+    return precision == 64 ? dispatch_dopri5<double>(m->pd, a, st) : dispatch_dopri5<float>(m->pf, a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipe micro-benchmarks: dependent-chain-free unrolled loops, enough warps to saturate the pipe
+template <int MODE>
+__global__ void __launch_bounds__(256) peak_kernel(float* sink, int iters, long long* clk) {
+    const long long c0 = clock64();
+    if (MODE == 0) {
+        float a[8], b = 1.0001f + threadIdx.x * 1e-7f, c = 0.5f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = i + threadIdx.x;
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], b, c);
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += a[i];
+        if (s == 12345.678f) sink[0] = s;
+    } else if (MODE == 1) {
+        double a[8], b = 1.0001 + threadIdx.x * 1e-9, c = 0.5;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = i + threadIdx.x;
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = fma(a[i], b, c);
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += a[i];
+        if (s == 12345.678) sink[0] = (float)s;
+    } else {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = 0.001f * (i + threadIdx.x);
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += a[i];
+        if (s == 12345.678f) sink[0] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) clk[MODE] = clock64() - c0;
+}
+
+extern "C" int pfr_measure_peaks(double out[4]) {
+    if (!out) return PFR_EINVAL;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* sink;
+    long long* clk;
+    CK(cudaMalloc((void**)&sink, 16));
+    CK(cudaMalloc((void**)&clk, 3 * sizeof(long long)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    const int iters[3] = {8192, 2048, 2048};
+    double clock_hz = 0;
+    for (int mode = 0; mode < 3; mode++) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(e0));
+            if (mode == 0) peak_kernel<0><<<blocks, threads>>>(sink, iters[0], clk);
+            else if (mode == 1) peak_kernel<1><<<blocks, threads>>>(sink, iters[1], clk);
+            else peak_kernel<2><<<blocks, threads>>>(sink, iters[2], clk);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK_LAUNCH("peak_kernel");
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = (double)blocks * threads * iters[mode] * 8.0;
+            const double rate = ops / (ms * 1e-3) * (mode == 2 ? 1.0 : 2.0);  // FMA = 2 flop
+            if (rep > 0 && rate > best) best = rate;
+            if (mode == 0 && rep == 3) {
+                long long hc[3];
+                CK(cudaMemcpy(hc, clk, sizeof(hc), cudaMemcpyDeviceToHost));
+                // one block's cycle count over the kernel's wall time (8 blocks/SM run concurrently)
+                clock_hz = (double)hc[0] / (ms * 1e-3);
+            }
+        }
+        out[mode] = best;
+    }
+    out[3] = clock_hz;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(clk);
+    return PFR_OK;
+}
+

@@ -1,0 +1,204 @@
+// The reference's 512-wide predictor MLPs, batched over conditions, plus the grid assembly around them.
+//
+//   fc4(relu(fc3(relu(fc2(relu(fc1(x)))))))      SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:192-208
+//                                                ...Eon_single_model.py:94-128
+//   x_k = (v_k - lo_k) / (hi_k - lo_k)           ...Eoff_single_model.py:282-300 (float32 tensor arithmetic)
+//   v = out * (max - min) + min                  ...Eoff_single_model.py:305   (float32 mul, then float32 add)
+//   enforce_strict                               ...Eoff_single_model.py:210-217, ...Eon_single_model.py:69-74
+//   idx_cut = argmin |t_full - t_end|            ...Eon_single_model.py:348-350
+//   c0 = P/(R_J T) / (0.7 MW_hex/MW_H2O + 1)     ...Eoff_single_model.py:45-55
+//
+// Layout: activations are kept "knot-major" -- H[k][m], condition index m contiguous -- so that the last
+// layer writes the [801][n] grids the integrator reads coalesced, and weight tiles (pre-transposed to
+// Wt[k][out] on upload) and activation tiles both stream into shared memory with 16-byte cp.async, no
+// transposition.  FP32 FFMA with a single accumulator per output, k ascending: a fixed, documented
+// summation order, because enforce_strict decisions hang on last-bit differences.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pfr {
+
+constexpr int MLP_HID = 512;
+constexpr int MLP_OUT = 800;
+constexpr int GEMM_BM = 128;   // outputs per CTA tile
+constexpr int GEMM_BN = 128;   // conditions per CTA tile
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct MlpInputScale {
+    float lo[4], span[4];  // x = (v - lo) / span, float32
+    float fullL, fullU;    // L, u0 used when the arrays are absent (…Eon_single_model.py:309)
+};
+
+// ---- layer 1 (K = in_dim <= 4) fused with the input scaling: H1[k][m] = relu(b1[k] + sum_i W1[k][i] x_i[m]) ----
+__global__ void __launch_bounds__(256)
+mlp_layer1_kernel(const float* __restrict__ W1 /*[512][in_dim]*/, const float* __restrict__ b1, int in_dim,
+                  MlpInputScale sc, const float* __restrict__ T, const float* __restrict__ P,
+                  const float* __restrict__ L, const float* __restrict__ U, int m_valid, int ld,
+                  float* __restrict__ H1 /*[512][ld]*/) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ld) return;
+    const int ms = m < m_valid ? m : m_valid - 1;  // pad columns replicate the last condition
+    float x[4];
+    x[0] = __fdiv_rn(__fsub_rn(T[ms], sc.lo[0]), sc.span[0]);
+    x[1] = __fdiv_rn(__fsub_rn(P[ms], sc.lo[1]), sc.span[1]);
+    x[2] = __fdiv_rn(__fsub_rn(L ? L[ms] : sc.fullL, sc.lo[2]), sc.span[2]);
+    x[3] = __fdiv_rn(__fsub_rn(U ? U[ms] : sc.fullU, sc.lo[3]), sc.span[3]);
+    for (int k = 0; k < MLP_HID; k++) {
+        float acc = 0.f;
+        for (int i = 0; i < in_dim; i++) acc = fmaf(x[i], W1[k * in_dim + i], acc);
+        acc += b1[k];
+        H1[(size_t)k * ld + m] = fmaxf(acc, 0.f);
+    }
+}
+
+// ---- hidden / output layers: out[o][m] = act(bias[o] + sum_k Wt[k][o] * Hin[k][m]) ----
+// kFinal: no ReLU; v = out * span + omin (separate float32 mul and add) stored with bounds checks.
+template <bool kFinal>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+mlp_gemm_kernel(const float* __restrict__ Wt /*[K][npad]*/, const float* __restrict__ bias /*[npad]*/,
+                const float* __restrict__ Hin /*[K][ld]*/, int K, int npad, int ld, float* __restrict__ out,
+                size_t out_ld, int nout_valid, int m_valid, float span, float omin) {
+    __shared__ __align__(16) float As[GEMM_STAGES][GEMM_BK][GEMM_BM];
+    __shared__ __align__(16) float Bs[GEMM_STAGES][GEMM_BK][GEMM_BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int o0 = blockIdx.x * GEMM_BM, m0 = blockIdx.y * GEMM_BN;
+
+    auto load_stage = [&](int stage, int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int idx = tid + r * GEMM_THREADS;
+            const int row = idx >> 5, c4 = (idx & 31) << 2;
+            cp_async16(&As[stage][row][c4], Wt + (size_t)(k0 + row) * npad + o0 + c4);
+            cp_async16(&Bs[stage][row][c4], Hin + (size_t)(k0 + row) * ld + m0 + c4);
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+    const int nk = K / GEMM_BK;
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s * GEMM_BK);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + GEMM_STAGES - 1;
+        if (nxt < nk) load_stage(nxt % GEMM_STAGES, nxt * GEMM_BK);
+        cp_async_commit();
+        const int st = kt % GEMM_STAGES;
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[st][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[st][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[st][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[st][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = o0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        const float bo = bias[o];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + h * 64 + tx * 4;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float s = acc[i][h * 4 + j] + bo;
+                v[j] = kFinal ? __fadd_rn(__fmul_rn(s, span), omin) : fmaxf(s, 0.f);
+            }
+            if (!kFinal) {
+                *reinterpret_cast<float4*>(&out[(size_t)o * out_ld + m]) = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (o < nout_valid) {
+                float* dst = &out[(size_t)o * out_ld + m];
+                if (m + 3 < m_valid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (m + j < m_valid) dst[j] = v[j];
+                }
+            }
+        }
+    }
+}
+
+// ---- enforce_strict over rows 1..800 of a [.][ld] grid, one condition per thread ----
+// g points at row 1 (the un-scaled MLP output); row0 (if given) receives t0 = 0; t_end (if given) the last knot.
+// write_back = false leaves the rows untouched (t_end-only mode on a scratch buffer).
+__global__ void __launch_bounds__(256)
+enforce_strict_kernel(float* __restrict__ g, size_t ld, int m, float* __restrict__ row0, float* __restrict__ t_end,
+                      int write_back) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float prev = 0.f;
+    if (row0) row0[i] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < MLP_OUT; k++) {
+        float v = g[(size_t)k * ld + i];
+        if (v <= prev) {
+            v = __fadd_rn(prev, 1e-5f);
+            if (write_back) g[(size_t)k * ld + i] = v;
+        }
+        prev = v;
+    }
+    if (t_end) t_end[i] = prev;
+}
+
+// ---- idx_cut[i] = first argmin_k |t_full[k][i] - t_end[i]| in float32 ----
+__global__ void __launch_bounds__(256)
+idx_cut_kernel(const float* __restrict__ t_full, size_t ld, const float* __restrict__ t_end, int m, int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float te = t_end[i];
+    float best = fabsf(__fsub_rn(t_full[i], te));
+    int bi = 0;
+#pragma unroll 8
+    for (int k = 1; k <= MLP_OUT; k++) {
+        const float d = fabsf(__fsub_rn(t_full[(size_t)k * ld + i], te));
+        if (d < best) { best = d; bi = k; }
+    }
+    idx[i] = bi;
+}
+
+// ---- row 0 of the temperature profile = T0 ----
+__global__ void __launch_bounds__(256) copy_row_kernel(const float* __restrict__ src, float* __restrict__ dst, int m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) dst[i] = src[i];
+}
+
+// ---- inlet n-hexane concentration ----
+__global__ void __launch_bounds__(256)
+inlet_kernel(const float* __restrict__ T, const float* __restrict__ P, int m, float rj, double factor, float* __restrict__ c0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float q = __fdiv_rn(P[i], __fmul_rn(rj, T[i]));
+    c0[i] = (float)((double)q * factor);
+}
+
+}  // namespace pfr

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's surrogate path, batched over conditions on one B200.
+
+Same names and argument meaning as the reference's call seams, so its drivers can be replayed:
+
+  calculate_spec_conc_0_list   SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:45-55
+  model_time / predict_time_profile / predict_temp_profile
+                               ...Eoff_single_model.py:296-318, ...Eon_single_model.py:257-273
+  Trainer.predict_n_ode        ...Eoff_single_model.py:175-186
+  crnn_predict                 ...Eon_single_model.py:153-156
+  main() sweep loops           ...Eoff_single_model.py:339-369, ...Eon_single_model.py:320-368
+
+PyTorch is used for device memory, streams and (in sweep.py) torch.distributed only; every computation
+is a kernel of the in-tree C-ABI library (include/crnn_pfr.h).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .containers import CRNNParams, MLPParams, ModelSet
+
+NS, NTOTAL = 9, 801
+TIME_IN_LO = (870.0, 1.0e5, 0.5, 2.5)   # ...Eoff_single_model.py:282-283
+TIME_IN_HI = (1150.0, 3.0e5, 1.0, 5.0)
+INFERENCE_CLAMPS = (1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # ...Eon_single_model.py:57-62
+TRAINING_WIDE_CLAMPS = (1.0e-6, 6.0e1, -1.0e1, 1.0e1, -1.0e5, 1.0e5)  # WIDE_Eoff_surrogate_model_training.py:39-53
+METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(x, device):
+    """1-D float32 device tensor from array-like (host inputs are copied; device tensors are used as they are)."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device, non_blocking=True)
+
+
+class CrnnModel:
+    """Device-side handle of one CRNN parameter set (crnn_model_create)."""
+
+    def __init__(self, params: CRNNParams, clamps=INFERENCE_CLAMPS):
+        self.params = params
+        self.clamps = tuple(float(c) for c in clamps)
+        h = ctypes.c_void_p()
+        f = lambda a: a.ctypes.data_as(_lib.c_float_p)
+        cl = (ctypes.c_double * 6)(*self.clamps)
+        _lib.check(_lib.lib().crnn_model_create(f(params.w_in), f(params.w_b), f(params.w_out), cl, ctypes.byref(h)),
+                   "crnn_model_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().crnn_model_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class MlpModel:
+    """Device-side handle of one 512-wide predictor MLP (pfr_mlp_create); weights are uploaded once."""
+
+    def __init__(self, params: MLPParams):
+        self.params = params
+        self.in_dim = params.in_dim
+        W = (_lib.c_float_p * 4)(*[a.ctypes.data_as(_lib.c_float_p) for a in params.w])
+        B = (_lib.c_float_p * 4)(*[a.ctypes.data_as(_lib.c_float_p) for a in params.b])
+        lo = (ctypes.c_double * self.in_dim)(*TIME_IN_LO[: self.in_dim])
+        hi = (ctypes.c_double * self.in_dim)(*TIME_IN_HI[: self.in_dim])
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().pfr_mlp_create(self.in_dim, W, B, params.out_min, params.out_max, lo, hi, ctypes.byref(h)),
+                   "pfr_mlp_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().pfr_mlp_destroy(self.handle)
+        except Exception:
+            pass
+
+
+@dataclass
+class SolveResult:
+    y: torch.Tensor            # [9, n] outlet state, clamped to [lb, ub]
+    status: torch.Tensor       # [n] int32, 0 = ok
+    stats: torch.Tensor        # [3, n] int32: accepted, rejected, rhs evaluations
+    dense: torch.Tensor | None = None   # [801, 9, n]
+    t_end: torch.Tensor | None = None   # [n]
+    idx_cut: torch.Tensor | None = None  # [n] (Eon)
+    tgrid: torch.Tensor | None = None    # [801, n]
+    Tprof: torch.Tensor | None = None    # [801, n]
+
+    def raise_on_failure(self):
+        bad = (self.status != 0).nonzero().flatten()
+        if bad.numel():
+            i = int(bad[0])
+            raise _lib.PfrError(f"{bad.numel()} trajectories failed; first: condition {i}: "
+                                f"{_lib.STATUS_TEXT.get(int(self.status[i]), '?')}")
+        return self
+
+
+class Surrogate:
+    """One model variant (CRNN + time MLP [+ temperature MLP]) resident on one GPU."""
+
+    def __init__(self, models: ModelSet, device: str | torch.device = "cuda", clamps=INFERENCE_CLAMPS, chunk: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.PfrError("no CUDA device: this package has no CPU path")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        self.models = models
+        self.energy_on = models.energy_on
+        self.chunk = int(chunk)
+        self.crnn = CrnnModel(models.crnn, clamps)
+        self.time_mlp = MlpModel(models.time_mlp)
+        self.temp_mlp = MlpModel(models.temp_mlp) if models.temp_mlp is not None else None
+        self._ws = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _workspace(self, n: int):
+        need = _lib.lib().pfr_mlp_workspace_bytes(n, self.chunk)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ a1
+    def inlet_concentration(self, T, P) -> torch.Tensor:
+        T, P = _f32(T, self.device), _f32(P, self.device)
+        c0 = torch.empty_like(T)
+        _lib.check(_lib.lib().pfr_inlet_concentration(_ptr(T), _ptr(P), T.numel(), _ptr(c0), _stream()), "pfr_inlet_concentration")
+        return c0
+
+    def calculate_spec_conc_0_list(self, T, P) -> torch.Tensor:
+        """[n, 9] float32 with only column ns-3 non-zero, as the reference returns it."""
+        c0 = self.inlet_concentration(T, P)
+        out = torch.zeros((c0.numel(), NS), dtype=torch.float32, device=self.device)
+        out[:, NS - 3] = c0
+        return out
+
+    # ------------------------------------------------------------------ a2-a5
+    def time_grid(self, T, P, L=None, u0=None, want_grid=True, want_end=False, raw=False):
+        """(tgrid[801,n] | None, t_end[n] | None).  L/u0 None -> the full-length grid at (1.0 m, 2.5 m/s)."""
+        T, P = _f32(T, self.device), _f32(P, self.device)
+        L = None if L is None else _f32(L, self.device)
+        u0 = None if u0 is None else _f32(u0, self.device)
+        n = T.numel()
+        ws = self._workspace(n)
+        grid = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device) if want_grid else None
+        tend = torch.empty(n, dtype=torch.float32, device=self.device) if want_end else None
+        _lib.check(_lib.lib().pfr_time_grid(self.time_mlp.handle, _ptr(T), _ptr(P), _ptr(L), _ptr(u0), n, _ptr(grid), _ptr(tend),
+                                            int(raw), _ptr(ws), ws.numel(), self.chunk, _stream()), "pfr_time_grid")
+        return grid, tend
+
+    def temp_profile(self, T, P, raw=False) -> torch.Tensor:
+        if self.temp_mlp is None:
+            raise _lib.PfrError("this model set has no temperature MLP (Eoff variant)")
+        T, P = _f32(T, self.device), _f32(P, self.device)
+        n = T.numel()
+        ws = self._workspace(n)
+        prof = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().pfr_temp_profile(self.temp_mlp.handle, _ptr(T), _ptr(P), n, _ptr(prof), int(raw), _ptr(ws),
+                                               ws.numel(), self.chunk, _stream()), "pfr_temp_profile")
+        return prof
+
+    def idx_cut(self, t_full: torch.Tensor, t_end: torch.Tensor) -> torch.Tensor:
+        n = t_end.numel()
+        idx = torch.empty(n, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().pfr_idx_cut(_ptr(t_full), _ptr(t_end), n, _ptr(idx), _stream()), "pfr_idx_cut")
+        return idx
+
+    # ------------------------------------------------------------------ a7
+    def rhs(self, T, u, precision=64) -> torch.Tensor:
+        """du[9, n] = CRNNFunc.forward at temperatures T[n] and states u[9, n]."""
+        dt = torch.float64 if precision == 64 else torch.float32
+        T = torch.as_tensor(T).to(self.device, dt).contiguous()
+        u = torch.as_tensor(u).to(self.device, dt).contiguous()
+        du = torch.empty_like(u)
+        _lib.check(_lib.lib().pfr_rhs(self.crnn.handle, T.numel(), _ptr(T), _ptr(u), _ptr(du), precision, _stream()), "pfr_rhs")
+        return du
+
+    # ------------------------------------------------------------------ a8, a9
+    def integrate(self, T0, c0, tgrid=None, Tprof=None, t_end=None, idx_end=None, perm=None, method="rodas4",
+                  precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0) -> SolveResult:
+        T0, c0 = _f32(T0, self.device), _f32(c0, self.device)
+        n = T0.numel()
+        dt = torch.float64 if precision == 64 else torch.float32
+        y = torch.empty((NS, n), dtype=dt, device=self.device)
+        yd = torch.empty((NTOTAL, NS, n), dtype=dt, device=self.device) if dense else None
+        status = torch.empty(n, dtype=torch.int32, device=self.device)
+        stats = torch.empty((3, n), dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().pfr_integrate(self.crnn.handle, METHODS[method], precision, n, _ptr(T0), _ptr(c0), _ptr(tgrid),
+                                            _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, _ptr(y),
+                                            _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
+        return SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
+
+    # ------------------------------------------------------------------ the sweep (hot path)
+    def sweep(self, T, P, L=None, u0=None, method="rodas4", precision=64, rtol=1e-6, atol=1e-6, sort=True,
+              keep_grids=False) -> SolveResult:
+        """Outlet species for a batch of conditions.
+
+        Eoff (...Eoff_single_model.py:339-369): time MLP at (T,P,L,u0) -> enforce_strict -> integrate at T = T0
+        to the last knot.  Eon (...Eon_single_model.py:296-354): temperature MLP + full-length time MLP at
+        (T,P,1.0,2.5) -> integrate; the outlet is the state at knot idx_cut = argmin|t_full - t_short[-1]|.
+        """
+        T, P = _f32(T, self.device), _f32(P, self.device)
+        L = None if L is None else _f32(L, self.device)
+        u0 = None if u0 is None else _f32(u0, self.device)
+        c0 = self.inlet_concentration(T, P)
+        if not self.energy_on:
+            if method == "dopri5" or keep_grids:
+                tgrid, tend = self.time_grid(T, P, L, u0, want_grid=keep_grids, want_end=True)
+            else:
+                tgrid, tend = self.time_grid(T, P, L, u0, want_grid=False, want_end=True)
+            perm = torch.argsort(T, descending=True).to(torch.int32) if sort else None
+            res = self.integrate(T, c0, t_end=tend, perm=perm, method=method, precision=precision, rtol=rtol, atol=atol)
+            res.tgrid = tgrid
+            return res
+        t_full, _ = self.time_grid(T, P, None, None, want_grid=True)
+        Tprof = self.temp_profile(T, P)
+        if L is None:
+            idx = torch.full((T.numel(),), NTOTAL - 1, dtype=torch.int32, device=self.device)
+            tend = t_full[NTOTAL - 1].clone()
+        else:
+            _, tend = self.time_grid(T, P, L, u0, want_grid=False, want_end=True)
+            idx = self.idx_cut(t_full, tend)
+        perm = torch.argsort(idx, descending=True).to(torch.int32) if sort else None
+        res = self.integrate(T, c0, tgrid=t_full, Tprof=Tprof, idx_end=idx, perm=perm, method=method, precision=precision,
+                             rtol=rtol, atol=atol)
+        res.t_end = tend
+        if not keep_grids:
+            res.tgrid = res.Tprof = None
+        return res
+
+    # ------------------------------------------------------------------ reference seams (dense trajectories)
+    def predict_n_ode(self, T, P, L=None, u0=None, method="rodas4", precision=64, rtol=1e-6, atol=1e-6) -> SolveResult:
+        """Trainer.predict_n_ode for every condition at once: dense [801, 9, n] trajectories on the MLP time grid.
+        Eoff: T(t) = T0.  Eon: compute_crnn_full_MODEL1 (full-length grid + temperature profile)."""
+        T, P = _f32(T, self.device), _f32(P, self.device)
+        c0 = self.inlet_concentration(T, P)
+        if self.energy_on:
+            tgrid, _ = self.time_grid(T, P, None, None)
+            Tprof = self.temp_profile(T, P)
+        else:
+            tgrid, _ = self.time_grid(T, P, L, u0)
+            Tprof = None
+        return self.integrate(T, c0, tgrid=tgrid, Tprof=Tprof, method=method, precision=precision, rtol=rtol, atol=atol, dense=True)
+
+    def crnn_predict(self, t_ar, T_ar, u0, method="rodas4", precision=64, rtol=1e-6, atol=1e-6) -> torch.Tensor:
+        """crnn_predict(t_ar, T_ar, u0, time_array=t_ar, w_in, w_b, w_out) -> [9, 801] for ONE condition.
+        u0 is the reference's 9-vector; only the n-hexane entry may be non-zero."""
+        t = _f32(t_ar, self.device).reshape(NTOTAL, 1).contiguous()
+        Tp = _f32(T_ar, self.device).reshape(NTOTAL, 1).contiguous()
+        u0 = np.asarray(u0.detach().cpu() if isinstance(u0, torch.Tensor) else u0, dtype=np.float32)
+        if np.any(np.delete(u0, NS - 3) != 0):
+            raise ValueError("only the n-hexane inlet concentration may be non-zero")
+        res = self.integrate(Tp[0], u0[NS - 3: NS - 2], tgrid=t, Tprof=Tp, method=method, precision=precision, rtol=rtol,
+                             atol=atol, dense=True)
+        res.raise_on_failure()
+        return res.dense[:, :, 0].T.contiguous()
+
+
+def measure_peaks() -> dict:
+    """Pipe micro-benchmarks (FP32 FFMA, FP64 DFMA, MUFU.EX2) on the current device."""
+    out = (ctypes.c_double * 4)()
+    _lib.check(_lib.lib().pfr_measure_peaks(out), "pfr_measure_peaks")
+    return {"ffma_flops": out[0], "dfma_flops": out[1], "mufu_ops": out[2], "sm_clock_hz": out[3]}

@@ -410,10 +410,11 @@ def element_nullspace(dtype=torch.float32) -> torch.Tensor:
 class ConverterSpec:
     """Which trainer's ParameterConverter: fits, clamps and slope formulas.
 
-    wide : WIDE_Eoff_surrogate_model_training.py:25-29,48-52,186-188
-    eoff : Eoff_surrogate_model_training.py (narrow clamps, same slope form with its own fits)
-    eon  : Eon_surrogate_model_training.py:287-327
+    form 'wide' : WIDE_Eoff_surrogate_model_training.py:25-29,48-52,186-188 (slope_reg = 0.5)
+    form 'eon'  : Eon_surrogate_model_training.py:287-327 (fits :31-40, clamps :51-56)
+    form 'eoff' : Eoff_surrogate_model_training.py:204-244 (as 'eon' but b_fit enters slope_Ea)
     """
+    form: str = "wide"
     A_fit: float = 18.42068
     b_fit: float = 2.112
     Ea_fit: float = 63.304
@@ -425,12 +426,29 @@ class ConverterSpec:
     A: tuple = (1.0, 21.0)
 
 
+def narrow_spec(form: str, b_fit: float, Ea_fit: float) -> ConverterSpec:
+    """Clamp set shared by the narrow-range Eon / Eoff trainers (Eon…:51-56, Eoff…:48-53)."""
+    return ConverterSpec(form=form, b_fit=b_fit, Ea_fit=Ea_fit, wout=(-2.0, 2.0), win=(0.0, 2.0), Ea=(10.0, 200.0),
+                         b=(-3.0, 3.0), A=(3.0, 21.0))
+
+
 def converter_slopes(spec: ConverterSpec):
     f32 = torch.float32
     A, b, Ea, reg = (torch.tensor(v, dtype=f32) for v in (spec.A_fit, spec.b_fit, spec.Ea_fit, spec.slope_reg))
-    slope_A = A * (A / (A + NR)) * reg
-    slope_b = b * ((A + b + NR) / (A + b + NR + NS)) * reg
-    slope_Ea = Ea * ((Ea + A + NR) / (Ea - NR)) * reg
+    if spec.form == "wide":
+        slope_A = A * (A / (A + NR)) * reg
+        slope_b = b * ((A + b + NR) / (A + b + NR + NS)) * reg
+        slope_Ea = Ea * ((Ea + A + NR) / (Ea - NR)) * reg
+    elif spec.form == "eon":
+        slope_A = A * (A / (A + NS + NR))
+        slope_b = b * ((A + b + NR) / (A + b + NR + NS))
+        slope_Ea = Ea * ((Ea + A + NS + NR) / (Ea - NS - NR))
+    elif spec.form == "eoff":
+        slope_A = A * (A / (A + NS + NR))
+        slope_b = b * ((A + b + NR) / (A + b + NR + NS))
+        slope_Ea = Ea * ((Ea + A + b + NS + NR) / (Ea - b - NS - NR))
+    else:
+        raise ValueError(spec.form)
     return slope_A, slope_b, slope_Ea
 
 
