@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Contract benchmark: PFR trajectories per second on the synthetic 1M-condition 4-D Latin-hypercube sweep.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's CPU path, oracle port, all host cores)
+
+One "step" = one pass of the surrogate hot path over one batch of 2^20 conditions per GPU (weak scaling):
+inlet concentration -> temperature MLP + time MLPs -> enforce_strict / idx_cut -> adaptive Rosenbrock
+integration -> outlet species [9, n] (+ the final gather when N > 1).  Headline workload: LLNL Eon (the
+coupled CRNN + temperature-profile MLP path), float64 state, rtol = atol = 1e-6 (the reference's
+tolerances).  The LLNL Eoff (isothermal) sweep is timed as well and reported under "variants".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden", "containers")
+METRIC = "PFR trajectories/sec (1M LHS conditions)"
+
+# FP64-pipe instruction counts per unit of algorithmic work (DESIGN.md "Roofline accounting"); 1 instr = 2 flop
+# so that the ratio to the measured DFMA peak (flop/s) is the FP64-pipe utilisation an ideal schedule would need.
+FP64_PER_TRANSCENDENTAL = 24          # CUDA libdevice log()/exp(), counted in the SASS of rhs_kernel<double>
+FP64_RHS = 2 * 81 + 18 * FP64_PER_TRANSCENDENTAL + 27          # two 9x9 mat-vecs, 9 log + 9 exp, clamps
+FP64_RHS_T = FP64_PER_TRANSCENDENTAL + 12 + 27                  # Eon only: ln T, 1/T, kT_j = lnA - Ea/RT + b lnT
+FP64_STEP = 9 * (18 + 81) + (204 + 36 + 9 * 6) + 6 * 81 + 2 * 135 + 60   # Jacobian, LU, 6 solves, stage sums, error norm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.th.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _flops(stats, energy_on):
+    """Algorithmic FP64 work of one integrator launch from its per-trajectory counters [3, n]."""
+    import torch
+    acc, rej, rhs = (stats[i].to(torch.float64).sum().item() for i in range(3))
+    instr = rhs * (FP64_RHS + (FP64_RHS_T if energy_on else 0)) + (acc + rej) * FP64_STEP
+    return 2.0 * instr, {"accepted_mean": acc / stats.shape[1], "rejected_mean": rej / stats.shape[1], "rhs_mean": rhs / stats.shape[1]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import Surrogate, measure_peaks
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import gather_outlets, lhs_conditions, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 under torchrun (python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_total = args.conditions_per_gpu * world
+    Th, Ph, Lh, Uh = lhs_conditions(n_total, seed=13895)
+    lo, hi = shard_bounds(n_total, world, rank)
+    host = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory() for a in (Th, Ph, Lh, Uh)]
+    n = hi - lo
+    T, P, L, U = (h.to(dev) for h in host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_steps(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.lib().pfr_launch_count()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, _lib.lib().pfr_launch_count() - l0
+
+    peaks = measure_peaks() if rank == 0 else None
+    result, variants = None, {}
+    for variant in ("Eon", "Eoff"):
+        sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), variant), device=dev)
+        kw = dict(method="rodas4", precision=args.precision, rtol=args.rtol, atol=args.atol)
+
+        def step_device():
+            r = sur.sweep(T, P, L, U, **kw)
+            r.y_all = gather_outlets(r.y, n_total)
+            return r
+
+        def step_e2e():
+            d = [h.to(dev, non_blocking=True) for h in host]
+            r = sur.sweep(*d, **kw)
+            y = gather_outlets(r.y, n_total)
+            r.y_host = y.to("cpu", non_blocking=False)
+            r.status_host = r.status.to("cpu")
+            return r
+
+        steps = args.steps if variant == "Eon" else max(1, min(args.steps, 3))
+        with ClockSampler(local) as clk:
+            ms, res, launches = time_steps(step_device, steps, args.warmup if variant == "Eon" else 3)
+        ms_e2e, res2, _ = time_steps(step_e2e, steps, 1)
+        bad = int((res.status != 0).sum().item())
+        flops, work = _flops(res.stats, variant == "Eon")
+        # the dominant kernel alone, on the stream it is launched on (torch's current stream)
+        if variant == "Eon":
+            tfull, _ = sur.time_grid(T, P)
+            Tp = sur.temp_profile(T, P)
+            perm = torch.argsort(res.idx_cut, descending=True).to(torch.int32)
+            c0 = sur.inlet_concentration(T, P)
+            kern = lambda: sur.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=res.idx_cut, perm=perm, **kw)
+        else:
+            perm = torch.argsort(T, descending=True).to(torch.int32)
+            c0 = sur.inlet_concentration(T, P)
+            tend = res.t_end
+            kern = lambda: sur.integrate(T, c0, t_end=tend, perm=perm, **kw)
+        kms, _, _ = time_steps(kern, 3, 1)
+        kms /= 3
+        entry = {
+            "value": n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "e2e": n_total * steps / (ms_e2e * 1e-3), "failed_trajectories": bad, "work_per_trajectory": work,
+            "integrator_ms": kms, "integrator_share_of_step": kms / (ms / steps),
+            "integrator_fp64_tflops": flops / (kms * 1e-3) / 1e12,
+        }
+        variants[f"LLNL_{variant}"] = entry
+        if variant == "Eon":
+            result = dict(entry=entry, clk=clk.summary(), launches=launches, flops=flops, kms=kms, steps=steps, ms=ms, ms_e2e=ms_e2e)
+        del sur
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    e = result["entry"]
+    peak = peaks["dfma_flops"]
+    line = {
+        "metric": METRIC, "value": e["value"], "unit": "trajectories/s", "n_gpus": world, "steps": result["steps"],
+        "warmup": args.warmup, "ms_per_step": e["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
+        "config": {"workload": "LLNL Eon CRNN + LLNL_2D temperature MLP + LLNL_4D_time_on MLP; 4-D Latin hypercube "
+                               "(T 870-1150 K, P 1-3 bar, L 0.5-1 m, u0 2.5-5 m/s), scipy qmc seed 13895",
+                   "conditions_per_gpu": args.conditions_per_gpu, "conditions_total": n_total, "integrator": "rodas4",
+                   "rtol": args.rtol, "atol": args.atol, "weights": "trained reference containers (tests/golden/containers)",
+                   "l2": "per-step working set (6.4 KB of grids per condition, 6.7 GB per GPU) exceeds the 126 MB L2",
+                   "parallelism": f"conditions sharded over {world} rank(s); final all-gather of [9,n] outlets only"},
+        "e2e": {"value": e["e2e"], "unit": "trajectories/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (72 if args.precision == 64 else 36) * n_total + 4 * n},
+        "gpu_launches": int(result["launches"]),
+        "clocks": result["clk"],
+        "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_kernel<double,ramp,knots>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
+                     "peak": peak / 1e12, "unit": "TFLOP/s", "frac": result["flops"] / (result["kms"] * 1e-3) / peak,
+                     "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
+                     "kernel_ms": result["kms"], "kernel_share_of_step": e["integrator_share_of_step"], "traffic": None,
+                     "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
+                                   f"Rosenbrock step overhead {FP64_STEP} (Jacobian, LU, 6 solves, stage sums); see DESIGN.md"},
+        "peaks_measured": {"ffma_tflops": peaks["ffma_flops"] / 1e12, "dfma_tflops": peaks["dfma_flops"] / 1e12, "mufu_tops": peaks["mufu_ops"] / 1e12},
+        "variants": variants,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, variant="Eon", sample=None):
+    """The oracle's restatement of the reference drivers (torch CPU ops, per-condition Python loop) on all host cores."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import lhs_conditions
+    from oracle import c_oracle as CO
+    from oracle import reference_driver as D
+    from oracle import reference_path as R
+
+    cores = os.cpu_count() or 1
+    sample = sample or 8 * cores
+    T, P, L, U = lhs_conditions(args.conditions_per_gpu, seed=13895)
+    idx = np.arange(0, len(T), len(T) // sample)[:sample]
+    ms = ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), variant)
+    t0 = time.time()
+    y = D.sweep_parallel(ms, T[idx], P[idx], L[idx], U[idx], cores)
+    dt = time.time() - t0
+    out = {"value": sample / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
+           "sample": f"{sample} of the {len(T)} LHS conditions (every {len(T) // sample}-th), LLNL {variant}, oracle/reference_driver.py "
+                     f"(torch CPU float32 ops, dopri5 1e-6/1e-6, 801 outputs, per-condition loop) over {cores} processes",
+           "seconds": dt, "failed": int(np.isnan(y).any(axis=1).sum())}
+    # for context: the same algorithm as compiled C (oracle/crnn_oracle.c), ODE part only, all cores
+    m = min(len(T), 8192)
+    sel = np.arange(0, len(T), len(T) // m)[:m]
+    tm = R.MLPParams(ms.time_mlp.w, ms.time_mlp.b, ms.time_mlp.out_min, ms.time_mlp.out_max)
+    pm = R.MLPParams(ms.temp_mlp.w, ms.temp_mlp.b, ms.temp_mlp.out_min, ms.temp_mlp.out_max)
+    t0 = time.time()
+    tg = R.time_grid(tm, T[sel], P[sel], np.full(m, 1.0, np.float32), np.full(m, 2.5, np.float32))
+    ts = R.time_grid(tm, T[sel], P[sel], L[sel], U[sel])
+    Tp = R.temp_profile(pm, T[sel], P[sel])
+    t_mlp = time.time() - t0
+    rep = np.array([R.eon_idx_cut(tg[i], ts[i, -1]) for i in range(m)], np.int32)
+    t0 = time.time()
+    CO.dopri5_batch(tg, Tp, R.inlet_concentration(T[sel], P[sel]), ms.crnn.w_in, ms.crnn.w_b, ms.crnn.w_out, report=rep, nthreads=cores)
+    t_ode = time.time() - t0
+    out["c_port_for_context"] = {"ode_trajectories_per_s": m / t_ode, "batched_torch_mlp_trajectories_per_s": m / t_mlp, "sample": m,
+                                 "note": "compiled C dopri5 (float32, 801 outputs) on all cores + batched torch-CPU MLPs; not what the reference runs"}
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, cb = [], None
+    for _ in range(args.warmup and 1):
+        cpu_baseline(args, sample=cores)
+    for _ in range(max(1, args.steps)):
+        cb = cpu_baseline(args, sample=4 * cores)
+        vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * 4 * cores / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LLNL Eon; the same 4-D Latin hypercube; bounded sample per step (see cpu_baseline.sample)",
+                       "note": "the reference scripts cannot run (torchdiffeq, cantera and the label files are absent): oracle port timed"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--conditions-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
+    ap.add_argument("--rtol", type=float, default=1e-6)
+    ap.add_argument("--atol", type=float, default=1e-6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ typedef struct pfr_mlp* pfr_mlp_t;
 int pfr_version(void);
 const char* pfr_status_string(int code);
 const char* pfr_last_cuda_error(void);
+/* number of kernels this library has launched in this process (monotone counter) */
+unsigned long long pfr_launch_count(void);
 
 /* CRNN parameters: `parameters[-1]` of a training history
  *   load_npz_parameters                      SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:223-230

@@ -29,6 +29,7 @@ def _declare(lib):
     lib.pfr_status_string.restype = ctypes.c_char_p
     lib.pfr_status_string.argtypes = [c_int]
     lib.pfr_last_cuda_error.restype = ctypes.c_char_p
+    lib.pfr_launch_count.restype = ctypes.c_ulonglong
     lib.crnn_model_create.argtypes = [c_float_p, c_float_p, c_float_p, c_double_p, ctypes.POINTER(c_void_p)]
     lib.crnn_model_destroy.argtypes = [c_void_p]
     lib.pfr_mlp_create.argtypes = [c_int, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), c_double, c_double,

@@ -17,6 +17,7 @@
 using namespace pfr;
 
 static thread_local char g_cuda_err[256] = "";
+static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py reports it)
 
 static int cuda_fail(cudaError_t e, const char* where) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
@@ -31,6 +32,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
     do {                                                       \
         cudaError_t e_ = cudaGetLastError();                   \
         if (e_ != cudaSuccess) return cuda_fail(e_, name);     \
+        g_launches++;                                          \
     } while (0)
 
 struct crnn_model {
@@ -67,6 +69,7 @@ extern "C" const char* pfr_status_string(int code) {
     }
 }
 extern "C" const char* pfr_last_cuda_error(void) { return g_cuda_err; }
+extern "C" unsigned long long pfr_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out) {
@@ -174,8 +177,8 @@ extern "C" size_t pfr_mlp_workspace_bytes(int n, int chunk) {
 }
 
 extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, float* c0, void* stream) {
-    if (!T || !P || !c0 || n < 0) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
+    if (!T || !P || !c0 || n < 0) return PFR_EINVAL;
     const double mw_hex = 6 * 12.011 + 14 * 1.008, mw_h2o = 2 * 1.008 + 15.999;  // Cantera 3.0 atomic weights
     const double factor = 1.0 / (0.7 * (mw_hex / mw_h2o) + 1);
     inlet_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, P, n, (float)8.314462618, factor, c0);
@@ -186,8 +189,8 @@ extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, fl
 // Shared driver of pfr_time_grid / pfr_temp_profile: chunks of `ld` conditions through the four layers.
 static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
                    float* t_end, bool is_time, int raw, void* ws, size_t ws_bytes, int chunk, cudaStream_t st) {
-    if (!m || !T || !P || n < 0 || (!grid && !t_end) || !ws) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
+    if (!m || !T || !P || n < 0 || (!grid && !t_end) || !ws) return PFR_EINVAL;
     const int ld = eff_chunk(n, chunk);
     if (ws_bytes < (2 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float)) return PFR_EWORKSPACE;
     float* H1 = static_cast<float*>(ws);
@@ -245,8 +248,8 @@ extern "C" int pfr_temp_profile(pfr_mlp_t mlp, const float* T, const float* P, i
 }
 
 extern "C" int pfr_idx_cut(const float* t_full, const float* t_end, int n, int* idx, void* stream) {
-    if (!t_full || !t_end || !idx || n < 0) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
+    if (!t_full || !t_end || !idx || n < 0) return PFR_EINVAL;
     idx_cut_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t_full, (size_t)n, t_end, n, idx);
     CK_LAUNCH("idx_cut_kernel");
     return PFR_OK;
@@ -269,8 +272,8 @@ rhs_kernel(const __grid_constant__ CrnnParams<real> p, int n, const real* __rest
 }
 
 extern "C" int pfr_rhs(crnn_model_t m, int n, const void* T, const void* u, void* du, int precision, void* stream) {
-    if (!m || !T || !u || !du || n < 0 || (precision != 32 && precision != 64)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
+    if (!m || !T || !u || !du || n < 0 || (precision != 32 && precision != 64)) return PFR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == 64)
         rhs_kernel<double><<<(n + 127) / 128, 128, 0, st>>>(m->pd, n, (const double*)T, (const double*)u, (double*)du);
@@ -315,6 +318,7 @@ static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaS
 extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
                   double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats, void* stream) {
+    if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
     if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5) return PFR_EINVAL;

@@ -27,6 +27,24 @@ def lib():
     return _LIB
 
 
+class use_fma_build:
+    """Context manager: route the calls below through the FMA-contracted build (ill-conditioning demo only)."""
+
+    def __enter__(self):
+        global _LIB
+        so = os.path.join(_HERE, "liboracle_fma.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "liboracle_fma.so"], stdout=subprocess.DEVNULL)
+        self._saved = lib()
+        _LIB = ctypes.CDLL(so)
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB
+        _LIB = self._saved
+        return False
+
+
 def _p(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
 

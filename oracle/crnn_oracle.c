@@ -44,7 +44,9 @@ static void parallel_for(int N, int nthreads, pf_body body, void *arg) {
 #define NTOT 801
 #define LB_ 1.0e-6
 #define UB_ 6.0e1
-#define RKCAL_ 1.9872036e-3
+/* the reference holds R_kcal in float32 (a float32 tensor in the Eoff script, a python scalar rounded to the
+ * tensor dtype in the Eon script), so the model constant IS the float32-rounded value, in every precision */
+#define RKCAL_ ((double)1.9872036e-3f)
 
 /* ---- float32 state (the reference's dtype) ---- */
 #define REAL float

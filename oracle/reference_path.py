@@ -44,7 +44,9 @@ import torch
 NS, NR, NTOTAL = 9, 9, 801
 LB, UB = 1.0e-6, 6.0e1
 INTER_MIN, INTER_MAX = -3.0e1, 3.0e1
-R_KCAL = 1.9872036e-3
+# the reference holds R_kcal in float32 (float32 tensor / python scalar rounded to the tensor dtype): the model
+# constant is the float32-rounded value in every precision
+R_KCAL = float(np.float32(1.9872036e-3))
 LL_DU, UL_DU = -1.0e5, 1.0e5
 STEAM_DILUTION_RATIO = 0.7
 R_J = 8.314462618

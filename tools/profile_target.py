@@ -1,0 +1,30 @@
+"""Small fixed workload for ncu captures: one Eon integrate, one Eoff integrate, the three MLP passes.
+Usage: python tools/profile_target.py [n] [precision]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet  # noqa: E402
+from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import Surrogate  # noqa: E402
+from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import lhs_conditions  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+    prec = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    gold = os.path.join(ROOT, "tests", "golden", "containers", "LLNL.npz")
+    T, P, L, U = (torch.as_tensor(a).cuda() for a in lhs_conditions(n, seed=13895))
+    on = Surrogate(ModelSet.from_packed(gold, "Eon"))
+    off = Surrogate(ModelSet.from_packed(gold, "Eoff"))
+    for _ in range(2):
+        r1 = on.sweep(T, P, L, U, precision=prec)
+        r2 = off.sweep(T, P, L, U, precision=prec)
+    torch.cuda.synchronize()
+    print("ok", float(r1.y.sum()), float(r2.y.sum()), int(r1.status.sum()), int(r2.status.sum()))
+
+
+if __name__ == "__main__":
+    main()
