@@ -33,8 +33,9 @@ extern "C" {
 #define PFR_ST_NONFINITE 2
 #define PFR_ST_UNDERFLOW 3
 
-#define PFR_METHOD_RODAS4 0 /* adaptive Rosenbrock, knot-aware (the product integrator) */
-#define PFR_METHOD_DOPRI5 1 /* torchdiffeq-semantics dopri5 (reference-behaviour mode) */
+#define PFR_METHOD_RODAS4 0     /* adaptive Rosenbrock, knot-aware (the product integrator): 3 lanes per condition */
+#define PFR_METHOD_DOPRI5 1     /* torchdiffeq-semantics dopri5 (reference-behaviour mode) */
+#define PFR_METHOD_RODAS4_TPC 2 /* the same Rosenbrock method, one thread per condition (LU parked in shared memory) */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;
@@ -98,6 +99,11 @@ int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float*
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
                   double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats,
                   void* stream);
+
+/* Parity hook for the table-driven double-precision log (kind 0, x positive normal) / exp (kind 1, |x| < 700)
+ * used inside the Rosenbrock kernel in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).
+ * x[n] -> y[n], device pointers. */
+int pfr_fastmath(int kind, int n, const double* x, double* y, void* stream);
 
 /* Pipe micro-benchmarks used as roofline denominators (synchronous; a few ms each).
  * out[0] FP32 FFMA flop/s, out[1] FP64 DFMA flop/s, out[2] MUFU.EX2 op/s, out[3] SM clock seen (Hz, from clock64). */

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libcrnn_pfr_b200.so")
 PFR_OK = 0
 METHOD_RODAS4 = 0
 METHOD_DOPRI5 = 1
+METHOD_RODAS4_TPC = 2
 STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow"}
 
 c_void_p, c_int, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
@@ -48,6 +49,8 @@ def _declare(lib):
                                   c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]
     lib.pfr_measure_peaks.argtypes = [c_double_p]
+    lib.pfr_fastmath.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pfr_fastmath.restype = c_int
     for name in ("crnn_model_create", "crnn_model_destroy", "pfr_mlp_create", "pfr_mlp_destroy",
                  "pfr_inlet_concentration", "pfr_time_grid", "pfr_temp_profile", "pfr_idx_cut", "pfr_rhs",
                  "pfr_integrate", "pfr_measure_peaks"):

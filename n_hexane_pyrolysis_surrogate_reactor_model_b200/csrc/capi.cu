@@ -12,6 +12,7 @@
 #include "crnn_device.cuh"
 #include "integrate_dopri5.cuh"
 #include "integrate_rodas.cuh"
+#include "integrate_rodas_coop.cuh"
 #include "mlp.cuh"
 
 using namespace pfr;
@@ -47,6 +48,25 @@ struct pfr_mlp {
     float span, omin;
     MlpInputScale sc;
 };
+
+// log / exp tables of fastmath.cuh, computed once per process in long double and kept in device memory
+static FastTables* g_tables = nullptr;
+static int ensure_tables() {
+    if (g_tables) return PFR_OK;
+    FastTables h;
+    for (int i = 0; i < LOGTAB_N; i++) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / LOGTAB_N;
+        const double inv = (double)(1.0L / c);
+        h.logtab[i].x = inv;
+        h.logtab[i].y = (double)(-logl((long double)inv));
+    }
+    for (int j = 0; j < EXPTAB_N; j++) h.exptab[j] = (double)powl(2.0L, (long double)j / EXPTAB_N);
+    FastTables* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(FastTables)));
+    CK(cudaMemcpy(d, &h, sizeof(FastTables), cudaMemcpyHostToDevice));
+    g_tables = d;
+    return PFR_OK;
+}
 
 constexpr int DEFAULT_CHUNK = 65536;
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -306,6 +326,21 @@ static int dispatch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStr
     return launch_rodas<real, false, false>(p, a, st);
 }
 
+template <typename real, bool kRamp, bool kKnots>
+static int launch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
+    const int blocks = (a.n + COOP_PER_BLOCK - 1) / COOP_PER_BLOCK;
+    rodas4_coop_kernel<real, kRamp, kKnots><<<blocks, COOP_BLOCK, 0, st>>>(p, a);
+    CK_LAUNCH("rodas4_coop_kernel");
+    return PFR_OK;
+}
+
+template <typename real>
+static int dispatch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
+    if (a.Tprof) return launch_rodas_coop<real, true, true>(p, a, st);
+    if (a.y_dense || a.idx_end) return launch_rodas_coop<real, false, true>(p, a, st);
+    return launch_rodas_coop<real, false, false>(p, a, st);
+}
+
 template <typename real>
 static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaStream_t st) {
     const int grid = (a.n + DOPRI_BLOCK - 1) / DOPRI_BLOCK;
@@ -321,18 +356,43 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
-    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC) return PFR_EINVAL;
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
     if (max_steps <= 0) max_steps = 1000000;
+    {
+        const int rc = ensure_tables();
+        if (rc != PFR_OK) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (method == PFR_METHOD_RODAS4) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables};
+        return precision == 64 ? dispatch_rodas_coop<double>(m->pd, a, st) : dispatch_rodas_coop<float>(m->pf, a, st);
+    }
+    if (method == PFR_METHOD_RODAS4_TPC) {
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables};
         return precision == 64 ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
     }
     Dopri5Args a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
     return precision == 64 ? dispatch_dopri5<double>(m->pd, a, st) : dispatch_dopri5<float>(m->pf, a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fastmath_kernel(const FastTables* __restrict__ ft, int kind, int n,
+                                                       const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = kind == 0 ? fast_log(x[i], ft->logtab) : fast_exp(x[i], ft->exptab);
+}
+
+extern "C" int pfr_fastmath(int kind, int n, const double* x, double* y, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!x || !y || n < 0 || (kind != 0 && kind != 1)) return PFR_EINVAL;
+    const int rc = ensure_tables();
+    if (rc != PFR_OK) return rc;
+    fastmath_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g_tables, kind, n, x, y);
+    CK_LAUNCH("fastmath_kernel");
+    return PFR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 // (the reference's dopri5 steps across the kinks and pays with rejected steps and ~1e-4 errors).
 #pragma once
 #include "crnn_device.cuh"
+#include "fastmath.cuh"
 
 namespace pfr {
 
@@ -38,6 +39,7 @@ struct RodasArgs {
     int* status;           // [n] 0 ok, 1 max steps, 2 non-finite, 3 step underflow
     int* stats;            // [3][n] accepted, rejected, rhs evaluations; or nullptr
     int max_steps;
+    const FastTables* tables;  // device copy of the log / exp tables (fastmath.cuh)
 };
 
 namespace rodas4 {

@@ -1,0 +1,434 @@
+// RODAS4 with three cooperating lanes per PFR condition (ten conditions per warp).
+//
+// Same method, same controller and same results as rodas4_kernel (integrate_rodas.cuh); different mapping.
+// Index i of every 9-vector (species, reactions, matrix rows) belongs to lane i % 3 of the group and sits in
+// slot i / 3 of that lane's registers, so a lane holds 3 species, 3 reactions and 3 rows of E = I/(h gamma) - J.
+// Nothing per-condition lives in shared memory:
+//   * the three rows of E are inverted in place by a distributed Gauss-Jordan sweep (pivot row broadcast by
+//     warp shuffles, no pivoting), after which each of the six stage solves is a 3x9 mat-vec
+//     with short dependency chains instead of a serial triangular substitution;
+//   * the right-hand side needs two 9-element all-gathers (ln Y and the rates r), also by shuffles.
+// Per lane that is ~90 live doubles instead of ~250, so three to four times as many warps fit on an SM and each
+// lane still has three independent log/exp chains in flight; the unrolled loop body is a third as long.
+// Control state (t, h, knot cursor) is replicated in the three lanes and computed from bit-identical inputs.
+#pragma once
+#include "crnn_device.cuh"
+#include "fastmath.cuh"
+#include "integrate_rodas.cuh"
+
+namespace pfr {
+
+constexpr int COOP_BLOCK = 128;
+constexpr int COOP_PER_WARP = 10;
+constexpr int COOP_PER_BLOCK = COOP_PER_WARP * (COOP_BLOCK / 32);
+#ifndef PFR_COOP_MINB
+#define PFR_COOP_MINB 3
+#endif
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename real>
+struct CoopParams {  // block-shared copy of the CRNN parameters: lanes of a group read different columns / rows
+    real nu[NS * NR];
+    real wout[NS * NR];
+    real Ea[NR], b[NR], lnA[NR];
+    FastTables ft;  // log / exp tables (used by the double instantiation)
+};
+
+// log / exp of the hot loop: table-driven in double (fastmath.cuh), CUDA's logf / expf in float
+template <typename real> __device__ __forceinline__ real c_log(real x, const CoopParams<real>& sp);
+template <> __device__ __forceinline__ double c_log<double>(double x, const CoopParams<double>& sp) { return fast_log(x, sp.ft.logtab); }
+template <> __device__ __forceinline__ float c_log<float>(float x, const CoopParams<float>&) { return logf(x); }
+template <typename real> __device__ __forceinline__ real c_exp(real x, const CoopParams<real>& sp);
+template <> __device__ __forceinline__ double c_exp<double>(double x, const CoopParams<double>& sp) { return fast_exp(x, sp.ft.exptab); }
+template <> __device__ __forceinline__ float c_exp<float>(float x, const CoopParams<float>&) { return expf(x); }
+
+// Parameter reads from the block-shared copy.  volatile: the values are loop-invariant, and without it the
+// compiler hoists all 54 of a lane's coefficients out of the step loop into registers (and then spills).
+template <typename real>
+__device__ __forceinline__ real ldp(const real* q) { return *reinterpret_cast<const volatile real*>(q); }
+
+template <typename real>
+__device__ __forceinline__ void gather9(const real (&own)[3], real (&all)[NS], int base) {
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) all[3 * m + s] = __shfl_sync(FULL, own[m], base + s);
+}
+
+// sum of one value per lane over the three lanes of a group, in a fixed order (bit-identical in every lane)
+template <typename real>
+__device__ __forceinline__ real group_sum(real v, int base) {
+    const real a = __shfl_sync(FULL, v, base), b = __shfl_sync(FULL, v, base + 1), c = __shfl_sync(FULL, v, base + 2);
+    return (a + b) + c;
+}
+
+template <typename real> __device__ __forceinline__ real fast_rcp(real x);
+template <> __device__ __forceinline__ float fast_rcp<float>(float x) { return __frcp_rn(x); }
+template <> __device__ __forceinline__ double fast_rcp<double>(double x) {
+    // MUFU.RCP64H seed + two Newton steps: full double precision for the normal, well-scaled arguments met here
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+template <typename real, bool WithDeriv>
+__device__ __forceinline__ void coop_arrhenius(const CoopParams<real>& sp, real inv_R, int l, real T, real (&kT)[3], real& mE_out,
+                                               real& invT_out) {
+    const real invT = fast_rcp<real>(T);
+    const real mE = -inv_R * invT;
+    const real lnT = c_log<real>(T, sp);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const int j = 3 * m + l;
+        kT[m] = fma(ldp(&sp.Ea[j]), mE, fma(ldp(&sp.b[j]), lnT, ldp(&sp.lnA[j])));
+    }
+    mE_out = mE;
+    invT_out = invT;
+}
+
+// du_own = f(y) for the lane's three species.  KeepJac also returns g (masked rates, all nine) and q for the
+// lane's species.
+template <typename real, bool KeepJac>
+__device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnParams<real>& p, int l, int base,
+                                         const real (&kT)[3], const real (&yin)[3], real (&du)[3], real (&g_all)[NS],
+                                         real (&q_own)[3]) {
+    real lnY[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const real Y = m_min(m_max(yin[m], p.lb), p.ub);
+        lnY[m] = c_log<real>(Y, sp);
+        if (KeepJac) q_own[m] = (yin[m] >= p.lb && yin[m] <= p.ub) ? fast_rcp<real>(Y) : real(0);
+    }
+    real lnY_all[NS];
+    gather9<real>(lnY, lnY_all, base);
+    real r[3], gm[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const int j = 3 * m + l;
+        real z = kT[m];
+#pragma unroll
+        for (int k = 0; k < NS; k++) z = fma(ldp(&sp.nu[k * NR + j]), lnY_all[k], z);
+        r[m] = c_exp<real>(m_min(m_max(z, p.zlo), p.zhi), sp);
+        if (KeepJac) gm[m] = (z >= p.zlo && z <= p.zhi) ? r[m] : real(0);
+    }
+    real r_all[NS];
+    gather9<real>(r, r_all, base);
+    if (KeepJac) gather9<real>(gm, g_all, base);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const int i = 3 * m + l;
+        real s = real(0);
+#pragma unroll
+        for (int j = 0; j < NR; j++) s = fma(ldp(&sp.wout[i * NR + j]), r_all[j], s);
+        du[m] = m_min(m_max(s, p.dulo), p.duhi);
+    }
+}
+
+// x_own = A_own * b, with b distributed like x
+template <typename real>
+__device__ __forceinline__ void coop_solve(const real (&A)[3][NS], real (&x)[3], int base) {
+    real b_all[NS];
+    gather9<real>(x, b_all, base);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        real s = real(0);
+#pragma unroll
+        for (int k = 0; k < NS; k++) s = fma(A[m][k], b_all[k], s);
+        x[m] = s;
+    }
+}
+
+template <typename real, bool kRamp, bool kKnots>
+__global__ void __launch_bounds__(COOP_BLOCK, PFR_COOP_MINB)
+rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+    using namespace rodas4;
+    static_assert(!kRamp || kKnots, "a temperature ramp needs knot-limited stepping");
+    __shared__ CoopParams<real> sp;
+    for (int e = threadIdx.x; e < NS * NR; e += COOP_BLOCK) {
+        sp.nu[e] = p.nu[e / NR][e % NR];
+        sp.wout[e] = p.wout[e / NR][e % NR];
+    }
+    if (threadIdx.x < NR) {
+        sp.Ea[threadIdx.x] = p.Ea[threadIdx.x];
+        sp.b[threadIdx.x] = p.b[threadIdx.x];
+        sp.lnA[threadIdx.x] = p.lnA[threadIdx.x];
+    }
+    if (sizeof(real) == 8) {
+        for (int e = threadIdx.x; e < LOGTAB_N; e += COOP_BLOCK) sp.ft.logtab[e] = a.tables->logtab[e];
+        for (int e = threadIdx.x; e < EXPTAB_N; e += COOP_BLOCK) sp.ft.exptab[e] = a.tables->exptab[e];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int grp = lane / 3, l = lane - 3 * (lane / 3);
+    const bool mirror = grp == COOP_PER_WARP;  // lanes 30, 31 shadow lanes 27, 28 so that every shuffle has a full warp
+    if (mirror) { grp = COOP_PER_WARP - 1; l = lane - 30; }
+    const int base = 3 * grp;
+    const int first = (blockIdx.x * (COOP_BLOCK / 32) + warp) * COOP_PER_WARP;
+    if (first >= a.n) return;  // warp-uniform
+    const int slot = first + grp;
+    const bool writer = !mirror && slot < a.n;
+    const int i = a.perm ? a.perm[slot < a.n ? slot : a.n - 1] : (slot < a.n ? slot : a.n - 1);
+    const size_t n = (size_t)a.n;
+    real* __restrict__ y_out = static_cast<real*>(a.y_out);
+    real* __restrict__ y_dense = static_cast<real*>(a.y_dense);
+    const bool dense = kKnots && (y_dense != nullptr);
+
+    real y[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) y[m] = (3 * m + l == NS - 3) ? real(a.c0[i]) : real(0);
+
+    const int kend = (kKnots && a.idx_end) ? a.idx_end[i] : NTOT - 1;
+    double t = kKnots ? (double)a.tgrid[i] : 0.0;
+    const double t_final = kKnots ? (double)a.tgrid[(size_t)kend * n + i]
+                                  : (a.t_end ? (double)a.t_end[i] : (double)a.tgrid[(size_t)(NTOT - 1) * n + i]);
+    if (dense && writer) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) y_dense[(size_t)(3 * m + l) * n + i] = m_min(m_max(y[m], p.lb), p.ub);
+    }
+    int kc = 0;
+    double tk = t, tk1 = kKnots ? (double)a.tgrid[n + i] : t_final;
+    real Tk = real(a.T0[i]), slope = real(0);
+    if (kRamp) {
+        Tk = real(a.Tprof[i]);
+        slope = (real(a.Tprof[n + i]) - Tk) / real(tk1 - tk);
+    }
+    real kT[3], mE, invT;
+    if (!kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk, kT, mE, invT);
+
+    const real rtol = real(a.rtol), atol = real(a.atol);
+    int nacc = 0, nrej = 0, nrhs = 0, status = 0;
+    double hprop = 0.0;
+    bool first_step = true;
+    bool done = (kend == 0) || !(t_final > t);
+
+    while (__any_sync(FULL, !done)) {
+        // ---------------- f0, df/dt, Jacobian rows at (t, y) ----------------
+        real ak1[3], fx[3], A[3][NS];
+        real g_all[NS], q_own[3];
+        if (kRamp) coop_arrhenius<real, true>(sp, p.inv_R, l, Tk + slope * real(t - tk), kT, mE, invT);
+        coop_rhs<real, true>(sp, p, l, base, kT, y, ak1, g_all, q_own);
+        if (first_step) {
+            real d0 = real(0), d1n = real(0);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const real isk = fast_rcp<real>(atol + rtol * m_abs(y[m]));
+                d0 = fma(y[m] * isk, y[m] * isk, d0);
+                d1n = fma(ak1[m] * isk, ak1[m] * isk, d1n);
+            }
+            d0 = m_sqrt<real>(group_sum<real>(d0, base) / real(NS));
+            d1n = m_sqrt<real>(group_sum<real>(d1n, base) / real(NS));
+            const double h0 = (d0 < real(1e-5) || d1n < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1n;
+            hprop = fmin(100.0 * h0, t_final - t);
+            first_step = false;
+        }
+        const double dist = tk1 - t;
+        const bool clip = hprop * 1.01 >= dist;
+        double hs = clip ? dist : hprop;
+        if (done) hs = 1.0;  // finished groups keep executing the warp's instructions on harmless numbers
+        const real h = real(hs);
+        const real ih = fast_rcp<real>(h);
+        if (kRamp) {
+            // df/dt = W_out (g o dkT/dT) dT/dt for the lane's species
+            real gd[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++) gd[j] = g_all[j] * ((p.b[j] - p.Ea[j] * mE) * invT);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                real s = real(0);
+#pragma unroll
+                for (int j = 0; j < NR; j++) s = fma(ldp(&sp.wout[(3 * m + l) * NR + j]), gd[j], s);
+                fx[m] = s * slope;
+                ak1[m] = fma(h * real(d1), fx[m], ak1[m]);
+            }
+        }
+        {
+            // rows of E for the lane's species: E[i][k] = delta_ik / (h gamma) - q_k sum_j (wout[i][j] g_j) nu[k][j]
+            const real fac = real(1.0 / gamma) * ih;
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                real G[NR];
+#pragma unroll
+                for (int j = 0; j < NR; j++) G[j] = ldp(&sp.wout[(3 * m + l) * NR + j]) * g_all[j];
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    real s = real(0);
+#pragma unroll
+                    for (int j = 0; j < NR; j++) s = fma(G[j], p.nu[k][j], s);
+                    A[m][k] = s;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                const real qk = __shfl_sync(FULL, q_own[k / 3], base + k % 3);
+#pragma unroll
+                for (int m = 0; m < 3; m++) A[m][k] = fma(-qk, A[m][k], (3 * m + l == k) ? fac : real(0));
+            }
+        }
+        // ---------------- in-place Gauss-Jordan inverse of E over the group's nine rows ----------------
+        bool lu_ok = true;
+#pragma unroll
+        for (int c = 0; c < NS; c++) {
+            const int oc = c % 3, mc = c / 3;
+            real prow[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) prow[k] = __shfl_sync(FULL, A[mc][k], base + oc);
+            lu_ok = lu_ok && (m_abs(prow[c]) > real(1e-30));
+            const real ip = fast_rcp<real>(prow[c]);
+#pragma unroll
+            for (int k = 0; k < NS; k++) prow[k] = (k == c) ? ip : prow[k] * ip;
+            const bool own_pivot = (l == oc);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const real f = A[m][c];
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const real upd = (k == c) ? -f * ip : fma(-f, prow[k], A[m][k]);
+                    A[m][k] = (m == mc && own_pivot) ? prow[k] : upd;
+                }
+            }
+        }
+
+        // ---------------- six stages ----------------
+        real ak2[3], ak3[3], ak4[3], ak5[3], er[3], ynew[3], dy[3], g_[NS], q_[3];
+        coop_solve<real>(A, ak1, base);
+
+#pragma unroll
+        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a21), ak1[m], y[m]);
+        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c2 * hs - tk), kT, mE, invT);
+        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const real s = fma(real(C21) * ih, ak1[m], dy[m]);
+            ak2[m] = kRamp ? fma(h * real(d2), fx[m], s) : s;
+        }
+        coop_solve<real>(A, ak2, base);
+
+#pragma unroll
+        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a32), ak2[m], fma(real(a31), ak1[m], y[m]));
+        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c3 * hs - tk), kT, mE, invT);
+        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const real s = fma(real(C31) * ih, ak1[m], fma(real(C32) * ih, ak2[m], dy[m]));
+            ak3[m] = kRamp ? fma(h * real(d3), fx[m], s) : s;
+        }
+        coop_solve<real>(A, ak3, base);
+
+#pragma unroll
+        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a43), ak3[m], fma(real(a42), ak2[m], fma(real(a41), ak1[m], y[m])));
+        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c4 * hs - tk), kT, mE, invT);
+        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const real s = fma(real(C41) * ih, ak1[m], fma(real(C42) * ih, ak2[m], fma(real(C43) * ih, ak3[m], dy[m])));
+            ak4[m] = kRamp ? fma(h * real(d4), fx[m], s) : s;
+        }
+        coop_solve<real>(A, ak4, base);
+
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+            ynew[m] = fma(real(a54), ak4[m], fma(real(a53), ak3[m], fma(real(a52), ak2[m], fma(real(a51), ak1[m], y[m]))));
+        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + hs - tk), kT, mE, invT);
+        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+            ak5[m] = fma(real(C51) * ih, ak1[m], fma(real(C52) * ih, ak2[m], fma(real(C53) * ih, ak3[m],
+                     fma(real(C54) * ih, ak4[m], dy[m]))));
+        coop_solve<real>(A, ak5, base);
+
+#pragma unroll
+        for (int m = 0; m < 3; m++) ynew[m] += ak5[m];  // embedded 3rd-order solution
+        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+            er[m] = fma(real(C61) * ih, ak1[m], fma(real(C62) * ih, ak2[m], fma(real(C63) * ih, ak3[m],
+                    fma(real(C64) * ih, ak4[m], fma(real(C65) * ih, ak5[m], dy[m])))));
+        coop_solve<real>(A, er, base);
+
+        // ---------------- error estimate and step-size control (replicated, bit-identical in the 3 lanes) ----
+        real e2 = real(0);
+        bool fin_own = true;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            ynew[m] += er[m];
+            const real sk = atol + rtol * m_max(m_abs(y[m]), m_abs(ynew[m]));
+            const real w = er[m] * fast_rcp<real>(sk);
+            e2 = fma(w, w, e2);
+            fin_own = fin_own && (m_abs(ynew[m]) < real(1e30));
+        }
+        const real err = m_sqrt<real>(group_sum<real>(e2, base) / real(NS));
+        const unsigned okmask = __ballot_sync(FULL, fin_own && lu_ok);
+        bool finite = ((okmask >> base) & 7u) == 7u;
+        finite = finite && (err == err) && (err < real(1e30));
+
+        if (!done) {
+            nrhs += 6;
+            if (finite && err <= real(1)) {
+                double f = err > real(0) ? 0.9 / sqrt(sqrt((double)err)) : 6.0;
+                f = fmin(6.0, fmax(0.2, f));
+                hprop = clip ? fmax(hprop, hs * f) : hs * f;
+                nacc++;
+#pragma unroll
+                for (int m = 0; m < 3; m++) y[m] = ynew[m];
+                if (clip) {
+                    t = tk1;
+                    if (kKnots) {
+                        kc++;
+                        if (dense && writer) {
+#pragma unroll
+                            for (int m = 0; m < 3; m++)
+                                y_dense[((size_t)kc * NS + 3 * m + l) * n + i] = m_min(m_max(y[m], p.lb), p.ub);
+                        }
+                        if (kc >= kend) {
+                            done = true;
+                        } else {
+                            tk = tk1;
+                            tk1 = (double)a.tgrid[(size_t)(kc + 1) * n + i];
+                            if (kRamp) {
+                                Tk = real(a.Tprof[(size_t)kc * n + i]);
+                                slope = (real(a.Tprof[(size_t)(kc + 1) * n + i]) - Tk) / real(tk1 - tk);
+                            }
+                        }
+                    } else {
+                        done = true;
+                    }
+                } else {
+                    t += hs;
+                }
+            } else {
+                nrej++;
+                const double f = finite ? fmax(0.2, 0.9 / sqrt(sqrt((double)err))) : 0.2;
+                hprop = hs * fmin(f, 0.9);
+                if (!(t + hprop > t) || hprop < 1e-300) { status = finite ? PFR_ST_UNDERFLOW_ : PFR_ST_NONFINITE_; done = true; }
+            }
+            if (!done && nacc + nrej >= a.max_steps) { status = PFR_ST_MAXSTEPS_; done = true; }
+        }
+    }
+
+    if (!writer) return;
+    real yf[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        yf[m] = m_min(m_max(y[m], p.lb), p.ub);
+        y_out[(size_t)(3 * m + l) * n + i] = yf[m];
+    }
+    if (l == 0) {
+        a.status[i] = status;
+        if (a.stats) {
+            a.stats[i] = nacc;
+            a.stats[n + i] = nrej;
+            a.stats[2 * n + i] = nrhs;
+        }
+    }
+    if (dense && kc < NTOT - 1) {
+        for (int kk = kc + 1; kk < NTOT; kk++)
+#pragma unroll
+            for (int m = 0; m < 3; m++) y_dense[((size_t)kk * NS + 3 * m + l) * n + i] = yf[m];
+    }
+}
+
+}  // namespace pfr

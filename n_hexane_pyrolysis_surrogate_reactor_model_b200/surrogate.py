@@ -28,7 +28,7 @@ TIME_IN_LO = (870.0, 1.0e5, 0.5, 2.5)   # ...Eoff_single_model.py:282-283
 TIME_IN_HI = (1150.0, 3.0e5, 1.0, 5.0)
 INFERENCE_CLAMPS = (1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # ...Eon_single_model.py:57-62
 TRAINING_WIDE_CLAMPS = (1.0e-6, 6.0e1, -1.0e1, 1.0e1, -1.0e5, 1.0e5)  # WIDE_Eoff_surrogate_model_training.py:39-53
-METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5}
+METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC}
 
 
 def _ptr(t):
@@ -269,6 +269,14 @@ class Surrogate:
                              atol=atol, dense=True)
         res.raise_on_failure()
         return res.dense[:, :, 0].T.contiguous()
+
+
+def fastmath(kind: str, x: torch.Tensor) -> torch.Tensor:
+    """The kernel's table-driven float64 log / exp on a CUDA tensor (parity hook)."""
+    x = x.to(dtype=torch.float64).contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().pfr_fastmath({"log": 0, "exp": 1}[kind], x.numel(), _ptr(x), _ptr(y), _stream()), "pfr_fastmath")
+    return y
 
 
 def measure_peaks() -> dict:

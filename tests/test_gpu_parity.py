@@ -54,6 +54,38 @@ def test_rhs_golden_anchor(surrogates, golden):
     assert np.max(rel_err(du, golden["Eoff/rhs0_f64"])) < 1e-11
 
 
+def test_fast_log_exp(surrogates):
+    """The table-driven float64 log / exp of the Rosenbrock kernel vs numpy (glibc, < 1 ulp): exp within 2 ulp of
+    the result, log within 2.5e-15 absolute over the clamped state range (1 ulp at |log| ~ 14) and within 4 ulp of
+    the result away from log ~ 0."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import fastmath
+    surrogates()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-6), np.log(60.0), 200000)), rng.uniform(0.5, 2.0, 50000),
+                        rng.uniform(300.0, 3000.0, 50000), [1e-6, 60.0, 1.0, 2.0, 0.5]])
+    got = fastmath("log", torch.as_tensor(x).cuda()).cpu().numpy()
+    ref = np.log(x)
+    assert np.max(np.abs(got - ref)) < 2.5e-15
+    big = np.abs(ref) > 0.05
+    assert np.max(np.abs(got - ref)[big] / np.abs(ref[big])) < 9e-16
+    z = np.concatenate([rng.uniform(-30.0, 30.0, 300000), [-30.0, 30.0, 0.0, -1e-300, 700.0, -700.0]])
+    got = fastmath("exp", torch.as_tensor(z).cuda()).cpu().numpy()
+    assert np.max(np.abs(got - np.exp(z)) / np.exp(z)) < 4.5e-16
+
+
+def test_rodas_three_lane_kernel_equals_thread_per_condition(surrogates, conditions):
+    """The two mappings of the same method (3 lanes per condition with shuffles / 1 thread with the LU parked in
+    shared memory) agree to 1e-9 at the reference tolerances and take the same number of steps almost everywhere
+    (they differ in the order of floating-point operations and in log/exp implementation only)."""
+    T, P, L, U = cond4(conditions)
+    s = surrogates("LLNL", "Eon")
+    a = s.sweep(T, P, L, U, method="rodas4")
+    b = s.sweep(T, P, L, U, method="rodas4_tpc")
+    assert int(a.status.abs().sum()) == 0 and int(b.status.abs().sum()) == 0
+    assert np.max(rel_err(a.y.cpu().numpy(), b.y.cpu().numpy())) < 1e-9
+    assert float((a.stats[0] == b.stats[0]).float().mean()) > 0.9
+
+
 # ----------------------------------------------------------------------------------------------- a2-a5
 @pytest.mark.parametrize("mech", ["LLNL", "JetSurf", "NUIG"])
 def test_time_mlp_raw_vs_torch_cpu(surrogates, model_sets, conditions, mech):

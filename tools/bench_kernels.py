@@ -49,11 +49,12 @@ def main():
             for srt in (False, True):
                 perm = torch.argsort(T, descending=True).to(torch.int32) if srt else None
                 for prec in (64, 32):
-                    ms, res = timed(lambda: s.integrate(T, c0, t_end=tend, perm=perm, precision=prec))
-                    st = res.stats.double()
-                    rep[f"Eoff/rodas_f{prec}_sort{int(srt)}_ms"] = ms
-                    rep[f"Eoff/rodas_f{prec}_steps"] = [float(st[0].mean()), float(st[1].mean()), float(st[2].mean()), float(st[0].max())]
-                    rep[f"Eoff/rodas_f{prec}_bad"] = int((res.status != 0).sum())
+                    for meth in ("rodas4", "rodas4_tpc"):
+                        ms, res = timed(lambda: s.integrate(T, c0, t_end=tend, perm=perm, precision=prec, method=meth))
+                        st = res.stats.double()
+                        rep[f"Eoff/{meth}_f{prec}_sort{int(srt)}_ms"] = ms
+                        rep[f"Eoff/{meth}_f{prec}_steps"] = [float(st[0].mean()), float(st[1].mean()), float(st[2].mean()), float(st[0].max())]
+                        rep[f"Eoff/{meth}_f{prec}_bad"] = int((res.status != 0).sum())
             perm = torch.argsort(T, descending=True).to(torch.int32)
             ms, res = timed(lambda: s.integrate(T, c0, t_end=tend, perm=perm, method="dopri5", precision=32))
             rep["Eoff/dopri5_f32_ms"] = ms
@@ -70,11 +71,15 @@ def main():
             for srt in (False, True):
                 perm = torch.argsort(idx, descending=True).to(torch.int32) if srt else None
                 for prec in (64, 32):
-                    ms, res = timed(lambda: s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, precision=prec), reps=2)
-                    st = res.stats.double()
-                    rep[f"Eon/rodas_f{prec}_sort{int(srt)}_ms"] = ms
-                    rep[f"Eon/rodas_f{prec}_steps"] = [float(st[0].mean()), float(st[1].mean()), float(st[2].mean()), float(st[0].max())]
-                    rep[f"Eon/rodas_f{prec}_bad"] = int((res.status != 0).sum())
+                    for meth in ("rodas4", "rodas4_tpc"):
+                        ms, res = timed(lambda: s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, precision=prec, method=meth), reps=2)
+                        st = res.stats.double()
+                        rep[f"Eon/{meth}_f{prec}_sort{int(srt)}_ms"] = ms
+                        rep[f"Eon/{meth}_f{prec}_steps"] = [float(st[0].mean()), float(st[1].mean()), float(st[2].mean()), float(st[0].max())]
+                        rep[f"Eon/{meth}_f{prec}_bad"] = int((res.status != 0).sum())
+                        if meth == "rodas4" and prec == 64 and srt:
+                            ref = s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, precision=64, method="rodas4_tpc")
+                            rep["Eon/coop_vs_tpc_maxrel"] = float(((res.y - ref.y).abs() / ref.y.abs().clamp_min(1e-3)).max())
             rep["Eon/idx_cut_mean"] = float(idx.double().mean())
             ms, res = timed(lambda: s.sweep(T, P, L, U), reps=2)
             rep["Eon/sweep_ms"] = ms
