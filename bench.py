@@ -27,12 +27,14 @@ sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden", "containers")
 METRIC = "PFR trajectories/sec (1M LHS conditions)"
 
-# FP64-pipe instruction counts per unit of algorithmic work (DESIGN.md "Roofline accounting"); 1 instr = 2 flop
-# so that the ratio to the measured DFMA peak (flop/s) is the FP64-pipe utilisation an ideal schedule would need.
-FP64_PER_TRANSCENDENTAL = 24          # CUDA libdevice log()/exp(), counted in the SASS of rhs_kernel<double>
-FP64_RHS = 2 * 81 + 18 * FP64_PER_TRANSCENDENTAL + 27          # two 9x9 mat-vecs, 9 log + 9 exp, clamps
-FP64_RHS_T = FP64_PER_TRANSCENDENTAL + 12 + 27                  # Eon only: ln T, 1/T, kT_j = lnA - Ea/RT + b lnT
-FP64_STEP = 9 * (18 + 81) + (204 + 36 + 9 * 6) + 6 * 81 + 2 * 135 + 60   # Jacobian, LU, 6 solves, stage sums, error norm
+# FP64-pipe instruction counts per unit of ALGORITHMIC work (DESIGN.md "Roofline accounting"), i.e. what one thread
+# that owned a whole condition would have to execute with the kernel's own log/exp (fastmath.cuh); 1 instruction
+# = 2 flop, so achieved / measured-DFMA-peak is the FP64-pipe utilisation a redundancy-free schedule would show.
+# The 3-lane kernel executes ~35 % more than this (replicated control flow, Gauss-Jordan instead of LU).
+FP64_LOG, FP64_EXP, FP64_RCP = 11, 10, 5                      # table-driven log / exp, MUFU.RCP64H + 2 Newton steps
+FP64_RHS = 2 * 81 + 9 * FP64_LOG + 9 * FP64_EXP + 27           # two 9x9 mat-vecs, 9 log + 9 exp, clamp compares
+FP64_RHS_T = FP64_LOG + FP64_RCP + 27                          # on a T ramp: ln T, 1/T, kT_j = lnA - Ea/RT + b lnT
+FP64_STEP = (81 + 729 + 81) + (204 + 36 + 9 * FP64_RCP) + 6 * 81 + (90 + 18 + 135 + 15) + 50   # J, LU, 6 solves, stage sums, norm
 
 
 class ClockSampler:
@@ -205,7 +207,7 @@ def run_ours(args):
         "e2e": {"value": e["e2e"], "unit": "trajectories/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (72 if args.precision == 64 else 36) * n_total + 4 * n},
         "gpu_launches": int(result["launches"]),
         "clocks": result["clk"],
-        "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_kernel<double,ramp,knots>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
+        "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_coop_kernel<double,ramp,knots>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
                      "peak": peak / 1e12, "unit": "TFLOP/s", "frac": result["flops"] / (result["kms"] * 1e-3) / peak,
                      "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
                      "kernel_ms": result["kms"], "kernel_share_of_step": e["integrator_share_of_step"], "traffic": None,

@@ -329,7 +329,8 @@ static int dispatch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStr
 template <typename real, bool kRamp, bool kKnots>
 static int launch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
     const int blocks = (a.n + COOP_PER_BLOCK - 1) / COOP_PER_BLOCK;
-    rodas4_coop_kernel<real, kRamp, kKnots><<<blocks, COOP_BLOCK, 0, st>>>(p, a);
+    const size_t dyn = PFR_AINV_SMEM ? (size_t)3 * NS * COOP_BLOCK * sizeof(real) : 0;
+    rodas4_coop_kernel<real, kRamp, kKnots><<<blocks, COOP_BLOCK, dyn, st>>>(p, a);
     CK_LAUNCH("rodas4_coop_kernel");
     return PFR_OK;
 }

@@ -24,6 +24,12 @@ constexpr int COOP_PER_BLOCK = COOP_PER_WARP * (COOP_BLOCK / 32);
 #ifndef PFR_COOP_MINB
 #define PFR_COOP_MINB 3
 #endif
+#ifndef PFR_DOT2
+#define PFR_DOT2 0   // 1: dot products on two accumulators
+#endif
+#ifndef PFR_AINV_SMEM
+#define PFR_AINV_SMEM 0   // 1: park the inverse in shared memory for the six solves
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 template <typename real>
@@ -89,6 +95,22 @@ __device__ __forceinline__ void coop_arrhenius(const CoopParams<real>& sp, real 
     invT_out = invT;
 }
 
+// s = init + sum_k a_k b_k, optionally on two accumulators (shorter dependent-FMA chain)
+#define PFR_DOT9(s_, init_, A_, B_)                                                  \
+    do {                                                                             \
+        if (PFR_DOT2) {                                                              \
+            real s0_ = fma(A_(0), B_(0), init_), s1_ = A_(1) * B_(1);                \
+            s0_ = fma(A_(2), B_(2), s0_); s1_ = fma(A_(3), B_(3), s1_);              \
+            s0_ = fma(A_(4), B_(4), s0_); s1_ = fma(A_(5), B_(5), s1_);              \
+            s0_ = fma(A_(6), B_(6), s0_); s1_ = fma(A_(7), B_(7), s1_);              \
+            s_ = fma(A_(8), B_(8), s0_) + s1_;                                       \
+        } else {                                                                     \
+            real s0_ = init_;                                                        \
+            _Pragma("unroll") for (int q_ = 0; q_ < 9; q_++) s0_ = fma(A_(q_), B_(q_), s0_); \
+            s_ = s0_;                                                                \
+        }                                                                            \
+    } while (0)
+
 // du_own = f(y) for the lane's three species.  KeepJac also returns g (masked rates, all nine) and q for the
 // lane's species.
 template <typename real, bool KeepJac>
@@ -108,9 +130,12 @@ __device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnP
 #pragma unroll
     for (int m = 0; m < 3; m++) {
         const int j = 3 * m + l;
-        real z = kT[m];
-#pragma unroll
-        for (int k = 0; k < NS; k++) z = fma(ldp(&sp.nu[k * NR + j]), lnY_all[k], z);
+        real z;
+#define A_(k) ldp(&sp.nu[(k) * NR + j])
+#define B_(k) lnY_all[k]
+        PFR_DOT9(z, kT[m], A_, B_);
+#undef A_
+#undef B_
         r[m] = c_exp<real>(m_min(m_max(z, p.zlo), p.zhi), sp);
         if (KeepJac) gm[m] = (z >= p.zlo && z <= p.zhi) ? r[m] : real(0);
     }
@@ -120,23 +145,33 @@ __device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnP
 #pragma unroll
     for (int m = 0; m < 3; m++) {
         const int i = 3 * m + l;
-        real s = real(0);
-#pragma unroll
-        for (int j = 0; j < NR; j++) s = fma(ldp(&sp.wout[i * NR + j]), r_all[j], s);
+        real s;
+#define A_(j) ldp(&sp.wout[i * NR + (j)])
+#define B_(j) r_all[j]
+        PFR_DOT9(s, real(0), A_, B_);
+#undef A_
+#undef B_
         du[m] = m_min(m_max(s, p.dulo), p.duhi);
     }
 }
 
 // x_own = A_own * b, with b distributed like x
 template <typename real>
-__device__ __forceinline__ void coop_solve(const real (&A)[3][NS], real (&x)[3], int base) {
+__device__ __forceinline__ void coop_solve(const real (&A)[3][NS], const real* Ainv, real (&x)[3], int base) {
     real b_all[NS];
     gather9<real>(x, b_all, base);
 #pragma unroll
     for (int m = 0; m < 3; m++) {
-        real s = real(0);
-#pragma unroll
-        for (int k = 0; k < NS; k++) s = fma(A[m][k], b_all[k], s);
+        real s;
+#if PFR_AINV_SMEM
+#define A_(k) ldp(Ainv + (m * NS + (k)) * COOP_BLOCK)
+#else
+#define A_(k) A[m][k]
+#endif
+#define B_(k) b_all[k]
+        PFR_DOT9(s, real(0), A_, B_);
+#undef A_
+#undef B_
         x[m] = s;
     }
 }
@@ -147,6 +182,12 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
     using namespace rodas4;
     static_assert(!kRamp || kKnots, "a temperature ramp needs knot-limited stepping");
     __shared__ CoopParams<real> sp;
+#if PFR_AINV_SMEM
+    extern __shared__ __align__(16) unsigned char coop_dyn[];  // [27][COOP_BLOCK] reals: each lane's rows of E^-1
+    real* const Ainv = reinterpret_cast<real*>(coop_dyn) + threadIdx.x;
+#else
+    real* const Ainv = nullptr;
+#endif
     for (int e = threadIdx.x; e < NS * NR; e += COOP_BLOCK) {
         sp.nu[e] = p.nu[e / NR][e % NR];
         sp.wout[e] = p.wout[e / NR][e % NR];
@@ -292,9 +333,16 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             }
         }
 
+#if PFR_AINV_SMEM
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int k = 0; k < NS; k++) Ainv[(m * NS + k) * COOP_BLOCK] = A[m][k];
+        asm volatile("" ::: "memory");  // the inverse leaves the register file here
+#endif
         // ---------------- six stages ----------------
         real ak2[3], ak3[3], ak4[3], ak5[3], er[3], ynew[3], dy[3], g_[NS], q_[3];
-        coop_solve<real>(A, ak1, base);
+        coop_solve<real>(A, Ainv, ak1, base);
 
 #pragma unroll
         for (int m = 0; m < 3; m++) ynew[m] = fma(real(a21), ak1[m], y[m]);
@@ -305,7 +353,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             const real s = fma(real(C21) * ih, ak1[m], dy[m]);
             ak2[m] = kRamp ? fma(h * real(d2), fx[m], s) : s;
         }
-        coop_solve<real>(A, ak2, base);
+        coop_solve<real>(A, Ainv, ak2, base);
 
 #pragma unroll
         for (int m = 0; m < 3; m++) ynew[m] = fma(real(a32), ak2[m], fma(real(a31), ak1[m], y[m]));
@@ -316,7 +364,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             const real s = fma(real(C31) * ih, ak1[m], fma(real(C32) * ih, ak2[m], dy[m]));
             ak3[m] = kRamp ? fma(h * real(d3), fx[m], s) : s;
         }
-        coop_solve<real>(A, ak3, base);
+        coop_solve<real>(A, Ainv, ak3, base);
 
 #pragma unroll
         for (int m = 0; m < 3; m++) ynew[m] = fma(real(a43), ak3[m], fma(real(a42), ak2[m], fma(real(a41), ak1[m], y[m])));
@@ -327,7 +375,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             const real s = fma(real(C41) * ih, ak1[m], fma(real(C42) * ih, ak2[m], fma(real(C43) * ih, ak3[m], dy[m])));
             ak4[m] = kRamp ? fma(h * real(d4), fx[m], s) : s;
         }
-        coop_solve<real>(A, ak4, base);
+        coop_solve<real>(A, Ainv, ak4, base);
 
 #pragma unroll
         for (int m = 0; m < 3; m++)
@@ -338,7 +386,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
         for (int m = 0; m < 3; m++)
             ak5[m] = fma(real(C51) * ih, ak1[m], fma(real(C52) * ih, ak2[m], fma(real(C53) * ih, ak3[m],
                      fma(real(C54) * ih, ak4[m], dy[m]))));
-        coop_solve<real>(A, ak5, base);
+        coop_solve<real>(A, Ainv, ak5, base);
 
 #pragma unroll
         for (int m = 0; m < 3; m++) ynew[m] += ak5[m];  // embedded 3rd-order solution
@@ -347,7 +395,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
         for (int m = 0; m < 3; m++)
             er[m] = fma(real(C61) * ih, ak1[m], fma(real(C62) * ih, ak2[m], fma(real(C63) * ih, ak3[m],
                     fma(real(C64) * ih, ak4[m], fma(real(C65) * ih, ak5[m], dy[m])))));
-        coop_solve<real>(A, er, base);
+        coop_solve<real>(A, Ainv, er, base);
 
         // ---------------- error estimate and step-size control (replicated, bit-identical in the 3 lanes) ----
         real e2 = real(0);
