@@ -210,7 +210,8 @@ def run_ours(args):
         "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_coop_kernel<double,ramp,knots>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
                      "peak": peak / 1e12, "unit": "TFLOP/s", "frac": result["flops"] / (result["kms"] * 1e-3) / peak,
                      "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
-                     "kernel_ms": result["kms"], "kernel_share_of_step": e["integrator_share_of_step"], "traffic": None,
+                     "kernel_ms": result["kms"], "kernel_share_of_step": e["integrator_share_of_step"],
+                     "traffic": 23.5e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01b_ncu_full_rodas4_coop_fp64.txt: 23.5 KB per condition x n",
                      "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
                                    f"Rosenbrock step overhead {FP64_STEP} (Jacobian, LU, 6 solves, stage sums); see DESIGN.md"},
         "peaks_measured": {"ffma_tflops": peaks["ffma_flops"] / 1e12, "dfma_tflops": peaks["dfma_flops"] / 1e12, "mufu_tops": peaks["mufu_ops"] / 1e12},
