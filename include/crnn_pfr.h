@@ -33,6 +33,8 @@ extern "C" {
 #define PFR_ST_NONFINITE 2
 #define PFR_ST_UNDERFLOW 3
 
+#define PFR_FLAG_DENSE_RAW 1
+
 #define PFR_METHOD_RODAS4 0     /* adaptive Rosenbrock, knot-aware (the product integrator): 3 lanes per condition */
 #define PFR_METHOD_DOPRI5 1     /* torchdiffeq-semantics dopri5 (reference-behaviour mode) */
 #define PFR_METHOD_RODAS4_TPC 2 /* the same Rosenbrock method, one thread per condition (LU parked in shared memory) */
@@ -94,11 +96,23 @@ int pfr_rhs(crnn_model_t m, int n, const void* T, const void* u, void* du, int p
  * y_out[9][n] (double for precision 64, float for 32), clamped to [lb, ub]; y_dense[801][9][n] or NULL
  * (requires tgrid); status[n]; stats[3][n] = accepted steps, rejected steps, RHS evaluations (or NULL).
  * perm[n] or NULL: thread j integrates condition perm[j] -- a cost-sorted order keeps the lanes of a warp in
- * step with each other; every array is still indexed by the condition, so outputs need no un-permuting. */
+ * step with each other; every array is still indexed by the condition, so outputs need no un-permuting.
+ * flags: PFR_FLAG_DENSE_RAW leaves y_dense unclamped (the training step needs the raw knot states). */
 int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
-                  double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats,
-                  void* stream);
+                  double rtol, double atol, int max_steps, int flags, void* y_out, void* y_dense, int* status,
+                  int* stats, void* stream);
+
+/* Loss and gradient of one training step for a batch of conditions
+ *   loss = Trainer.loss_n_ode(p, i_exp); loss.backward()   SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py:387-396,414-416
+ * y_knots[801][9][n]: raw knot states of the forward pass (pfr_integrate with y_dense and PFR_FLAG_DENSE_RAW, double);
+ * ref[801][7][n] labels (mol/m3), yscale[7][n] (...:105).  loss[n]: per-condition MSE over 7 x 801 points;
+ * grad[189][n]: per-condition d loss / d (w_in[11][9] | w_b[9] | w_out[9][9]) by the continuous adjoint, RK4 with
+ * `substeps` steps per knot interval.  The model's clamps are those given to crnn_model_create. */
+int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof, const double* y_knots,
+                  const float* ref, const float* yscale, int substeps, double* loss, double* grad, void* stream);
+/* out[r] = sum_i x[r][i] with a fixed summation tree (deterministic reduction of per-condition gradients) */
+int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream);
 
 /* Parity hook for the table-driven double-precision log (kind 0, x positive normal) / exp (kind 1, |x| < 700)
  * used inside the Rosenbrock kernel in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).

@@ -1,0 +1,215 @@
+// Loss and parameter gradient of one CRNN training step, one condition per thread.
+//
+// Replaces  loss = Trainer.loss_n_ode(p, i_exp); loss.backward()
+//   (SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py:387-396, 414-416)
+// for a whole batch of conditions.  The reference back-propagates through every operation of torchdiffeq's
+// dopri5; here the gradient with respect to the CRNN parameters (w_in[11][9], w_b[9], w_out[9][9]) is the
+// continuous adjoint of the same loss:
+//     L      = mean_{i<7, k<=800} ((clamp(y_i(t_k)) - ref_ik) / yscale_i)^2
+//     lam'   = -J(y,T)^T lam  between knots,   lam(t_k^-) = lam(t_k^+) + dL/dy(t_k),   lam(t_800^+) = 0
+//     dL/dth = sum over knot intervals of  integral lam^T df/dth dt
+// integrated backwards knot interval by knot interval with classical RK4 (`substeps` per interval); inside an
+// interval y(t) is the cubic Hermite interpolant of the forward pass' knot states (the intervals are ~1/800 of
+// the residence time, h*lambda <= 0.1) and T(t) is the same linear ramp the forward pass saw.
+// df/dth contracts to outer products:  with lt_i = lam_i [du_i unclamped],  mu_j = [z_j unclamped] r_j sum_i lt_i wout_ij :
+//     d/dwout_ij = lt_i r_j      d/dwb_j = mu_j      d/dwin_kj = mu_j wv_k      (J^T lam)_k = q_k sum_j nu_kj mu_j
+// The 189 accumulators of a condition live in the thread's local memory (a training batch is hundreds of
+// conditions, not millions; the arrays stay in L1).
+#pragma once
+#include "crnn_device.cuh"
+
+namespace pfr {
+
+constexpr int NPAR = 11 * NR + NR + NS * NR;  // 189: w_in | w_b | w_out
+constexpr int NOBS = 7;                       // observed species i_obs = 0..6
+constexpr int ADJ_BLOCK = 64;
+
+struct AdjointArgs {
+    int n;
+    const float* T0;        // [n]
+    const float* tgrid;     // [801][n]
+    const float* Tprof;     // [801][n] or nullptr (T = T0)
+    const double* y_knots;  // [801][9][n] forward states at the knots, NOT clamped
+    const float* ref;       // [801][7][n] labels (mol/m3)
+    const float* yscale;    // [7][n]
+    int substeps;
+    double* loss;           // [n] per-condition MSE
+    double* grad;           // [189][n] per-condition gradient
+};
+
+struct AdjNode {
+    double r[NR], mz[NR], wv[NS + 2], q[NS], md[NS];
+};
+
+// forward quantities of the RHS at (T, y): rates, masks, the input vector wv = [ln Y ; -1/(R T) ; ln T]
+__device__ __forceinline__ void adj_forward(const CrnnParams<double>& p, double T, const double (&y)[NS], AdjNode& nd, double (&f)[NS]) {
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        const double Y = m_min(m_max(y[k], p.lb), p.ub);
+        nd.wv[k] = log(Y);
+        nd.q[k] = (y[k] >= p.lb && y[k] <= p.ub) ? 1.0 / Y : 0.0;
+    }
+    nd.wv[NS] = -p.inv_R / T;
+    nd.wv[NS + 1] = log(T);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        double z = fma(p.Ea[j], nd.wv[NS], fma(p.b[j], nd.wv[NS + 1], p.lnA[j]));
+#pragma unroll
+        for (int k = 0; k < NS; k++) z = fma(p.nu[k][j], nd.wv[k], z);
+        nd.r[j] = exp(m_min(m_max(z, p.zlo), p.zhi));
+        nd.mz[j] = (z >= p.zlo && z <= p.zhi) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NR; j++) s = fma(p.wout[i][j], nd.r[j], s);
+        f[i] = m_min(m_max(s, p.dulo), p.duhi);
+        nd.md[i] = (s >= p.dulo && s <= p.duhi) ? 1.0 : 0.0;
+    }
+}
+
+// J^T lam, and G += w * lam^T df/dtheta
+__device__ __forceinline__ void adj_contract(const CrnnParams<double>& p, const AdjNode& nd, const double (&lam)[NS], double w,
+                                             double* __restrict__ G, double (&Jtl)[NS]) {
+    double lt[NS], mu[NR];
+#pragma unroll
+    for (int i = 0; i < NS; i++) lt[i] = lam[i] * nd.md[i];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) s = fma(lt[i], p.wout[i][j], s);
+        mu[j] = s * nd.r[j] * nd.mz[j];
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NR; j++) s = fma(p.nu[k][j], mu[j], s);
+        Jtl[k] = s * nd.q[k];
+    }
+    // w_in [11][9]
+    for (int k = 0; k < NS + 2; k++) {
+        const double wk = w * nd.wv[k];
+#pragma unroll
+        for (int j = 0; j < NR; j++) G[k * NR + j] = fma(wk, mu[j], G[k * NR + j]);
+    }
+    // w_b [9]
+#pragma unroll
+    for (int j = 0; j < NR; j++) G[11 * NR + j] = fma(w, mu[j], G[11 * NR + j]);
+    // w_out [9][9]
+    for (int i = 0; i < NS; i++) {
+        const double wl = w * lt[i];
+#pragma unroll
+        for (int j = 0; j < NR; j++) G[12 * NR + i * NR + j] = fma(wl, nd.r[j], G[12 * NR + i * NR + j]);
+    }
+}
+
+template <bool kRamp>
+__global__ void __launch_bounds__(ADJ_BLOCK)
+adjoint_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointArgs a) {
+    const int i = blockIdx.x * ADJ_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    const size_t n = (size_t)a.n;
+    double G[NPAR];
+    for (int e = 0; e < NPAR; e++) G[e] = 0.0;
+    double lam[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) lam[k] = 0.0;
+    double sc[NOBS];
+#pragma unroll
+    for (int s = 0; s < NOBS; s++) sc[s] = (double)a.yscale[(size_t)s * n + i];
+    const double wnorm = 1.0 / (double)(NOBS * NTOT);
+    const double T0 = (double)a.T0[i];
+    double loss = 0.0;
+
+    double yb[NS], fb[NS];
+    AdjNode nd;
+    double tb = (double)a.tgrid[(size_t)(NTOT - 1) * n + i];
+    double Tb = kRamp ? (double)a.Tprof[(size_t)(NTOT - 1) * n + i] : T0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) yb[k] = a.y_knots[((size_t)(NTOT - 1) * NS + k) * n + i];
+    adj_forward(p, Tb, yb, nd, fb);
+
+    for (int kk = NTOT - 1; kk >= 0; kk--) {
+        // jump of the adjoint at knot kk: dL/dy(t_kk) through the output clamp
+#pragma unroll
+        for (int s = 0; s < NOBS; s++) {
+            const double pc = m_min(m_max(yb[s], p.lb), p.ub);
+            const double d = (pc - (double)a.ref[((size_t)kk * NOBS + s) * n + i]) / sc[s];
+            loss = fma(d, d, loss);
+            if (yb[s] >= p.lb && yb[s] <= p.ub) lam[s] += 2.0 * d / sc[s] * wnorm;
+        }
+        if (kk == 0) break;
+        // interval [ta, tb]
+        const double ta = (double)a.tgrid[(size_t)(kk - 1) * n + i];
+        const double Ta = kRamp ? (double)a.Tprof[(size_t)(kk - 1) * n + i] : T0;
+        double ya[NS], fa[NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) ya[k] = a.y_knots[((size_t)(kk - 1) * NS + k) * n + i];
+        AdjNode nda;
+        adj_forward(p, Ta, ya, nda, fa);
+        const double h = tb - ta;
+        const double slope = (Tb - Ta) / h;
+        const double hs = h / (double)a.substeps;
+
+        auto node_at = [&](double tau, AdjNode& out) {
+            // cubic Hermite state and ramp temperature at tau in [ta, tb]
+            const double s = (tau - ta) / h, s2 = s * s, s3 = s2 * s;
+            const double h00 = 2 * s3 - 3 * s2 + 1, h10 = s3 - 2 * s2 + s, h01 = -2 * s3 + 3 * s2, h11 = s3 - s2;
+            double yy[NS], ff[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) yy[k] = h00 * ya[k] + h10 * h * fa[k] + h01 * yb[k] + h11 * h * fb[k];
+            adj_forward(p, kRamp ? Ta + slope * (tau - ta) : T0, yy, out, ff);
+        };
+
+        for (int ss = 0; ss < a.substeps; ss++) {
+            const double tau1 = tb - ss * hs;
+            const bool last = (ss == a.substeps - 1);
+            double k1[NS], k2[NS], k3[NS], k4[NS], l2[NS];
+            AdjNode nm;
+            // stage 1 at tau1: `nd` always holds the node at the upper end of the current sub-step
+            adj_contract(p, nd, lam, hs / 6.0, G, k1);
+            // stages 2, 3 at the midpoint
+            node_at(tau1 - 0.5 * hs, nm);
+#pragma unroll
+            for (int k = 0; k < NS; k++) l2[k] = fma(0.5 * hs, k1[k], lam[k]);
+            adj_contract(p, nm, l2, hs / 3.0, G, k2);
+#pragma unroll
+            for (int k = 0; k < NS; k++) l2[k] = fma(0.5 * hs, k2[k], lam[k]);
+            adj_contract(p, nm, l2, hs / 3.0, G, k3);
+            // stage 4 at tau0
+            if (last) nd = nda; else node_at(tau1 - hs, nd);
+#pragma unroll
+            for (int k = 0; k < NS; k++) l2[k] = fma(hs, k3[k], lam[k]);
+            adj_contract(p, nd, l2, hs / 6.0, G, k4);
+#pragma unroll
+            for (int k = 0; k < NS; k++) lam[k] += hs / 6.0 * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
+        }
+        // move to the next interval down: knot kk-1 becomes the upper end (nd already holds its node)
+#pragma unroll
+        for (int k = 0; k < NS; k++) { yb[k] = ya[k]; fb[k] = fa[k]; }
+        tb = ta;
+        Tb = Ta;
+    }
+    a.loss[i] = loss * wnorm;
+    for (int e = 0; e < NPAR; e++) a.grad[(size_t)e * n + i] = G[e];
+}
+
+// out[r] = sum_i x[r][i], fixed summation tree (deterministic): one block per row
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restrict__ x, int n, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const double* row = x + (size_t)blockIdx.x * n;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += row[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+}  // namespace pfr

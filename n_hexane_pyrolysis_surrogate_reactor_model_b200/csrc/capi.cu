@@ -13,6 +13,7 @@
 #include "integrate_dopri5.cuh"
 #include "integrate_rodas.cuh"
 #include "integrate_rodas_coop.cuh"
+#include "adjoint.cuh"
 #include "mlp.cuh"
 
 using namespace pfr;
@@ -353,7 +354,7 @@ static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaS
 
 extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
-                  double rtol, double atol, int max_steps, void* y_out, void* y_dense, int* status, int* stats, void* stream) {
+                  double rtol, double atol, int max_steps, int flags, void* y_out, void* y_dense, int* status, int* stats, void* stream) {
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
@@ -368,15 +369,37 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (method == PFR_METHOD_RODAS4) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables};
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
         return precision == 64 ? dispatch_rodas_coop<double>(m->pd, a, st) : dispatch_rodas_coop<float>(m->pf, a, st);
     }
     if (method == PFR_METHOD_RODAS4_TPC) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables};
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
         return precision == 64 ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
     }
     Dopri5Args a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
     return precision == 64 ? dispatch_dopri5<double>(m->pd, a, st) : dispatch_dopri5<float>(m->pf, a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof,
+                             const double* y_knots, const float* ref, const float* yscale, int substeps, double* loss,
+                             double* grad, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || n < 0 || substeps < 1) return PFR_EINVAL;
+    AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad};
+    const int blocks = (n + ADJ_BLOCK - 1) / ADJ_BLOCK;
+    if (Tprof) adjoint_kernel<true><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
+    else adjoint_kernel<false><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
+    CK_LAUNCH("adjoint_kernel");
+    return PFR_OK;
+}
+
+extern "C" int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream) {
+    if (rows == 0) return PFR_OK;
+    if (!x || !out || rows < 0 || n < 0) return PFR_EINVAL;
+    reduce_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    CK_LAUNCH("reduce_rows_kernel");
+    return PFR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

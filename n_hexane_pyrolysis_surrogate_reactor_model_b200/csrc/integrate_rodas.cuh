@@ -40,6 +40,7 @@ struct RodasArgs {
     int* stats;            // [3][n] accepted, rejected, rhs evaluations; or nullptr
     int max_steps;
     const FastTables* tables;  // device copy of the log / exp tables (fastmath.cuh)
+    int flags;                 // bit 0: y_dense holds the raw (unclamped) knot states
 };
 
 namespace rodas4 {
@@ -354,7 +355,7 @@ rodas4_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                     if (dense) {
 #pragma unroll
                         for (int k = 0; k < NS; k++)
-                            y_dense[((size_t)kc * NS + k) * n + i] = m_min(m_max(ynew[k], p.lb), p.ub);
+                            y_dense[((size_t)kc * NS + k) * n + i] = (a.flags & 1) ? ynew[k] : m_min(m_max(ynew[k], p.lb), p.ub);
                     }
                     if (kc >= kend) {
                         done = true;

@@ -228,7 +228,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
                                   : (a.t_end ? (double)a.t_end[i] : (double)a.tgrid[(size_t)(NTOT - 1) * n + i]);
     if (dense && writer) {
 #pragma unroll
-        for (int m = 0; m < 3; m++) y_dense[(size_t)(3 * m + l) * n + i] = m_min(m_max(y[m], p.lb), p.ub);
+        for (int m = 0; m < 3; m++) y_dense[(size_t)(3 * m + l) * n + i] = (a.flags & 1) ? y[m] : m_min(m_max(y[m], p.lb), p.ub);
     }
     int kc = 0;
     double tk = t, tk1 = kKnots ? (double)a.tgrid[n + i] : t_final;
@@ -429,7 +429,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
                         if (dense && writer) {
 #pragma unroll
                             for (int m = 0; m < 3; m++)
-                                y_dense[((size_t)kc * NS + 3 * m + l) * n + i] = m_min(m_max(y[m], p.lb), p.ub);
+                                y_dense[((size_t)kc * NS + 3 * m + l) * n + i] = (a.flags & 1) ? y[m] : m_min(m_max(y[m], p.lb), p.ub);
                         }
                         if (kc >= kend) {
                             done = true;

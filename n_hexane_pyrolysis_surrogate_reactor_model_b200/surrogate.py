@@ -192,7 +192,7 @@ class Surrogate:
 
     # ------------------------------------------------------------------ a8, a9
     def integrate(self, T0, c0, tgrid=None, Tprof=None, t_end=None, idx_end=None, perm=None, method="rodas4",
-                  precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0) -> SolveResult:
+                  precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0, dense_raw=False) -> SolveResult:
         T0, c0 = _f32(T0, self.device), _f32(c0, self.device)
         n = T0.numel()
         dt = torch.float64 if precision == 64 else torch.float32
@@ -201,7 +201,7 @@ class Surrogate:
         status = torch.empty(n, dtype=torch.int32, device=self.device)
         stats = torch.empty((3, n), dtype=torch.int32, device=self.device)
         _lib.check(_lib.lib().pfr_integrate(self.crnn.handle, METHODS[method], precision, n, _ptr(T0), _ptr(c0), _ptr(tgrid),
-                                            _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, _ptr(y),
+                                            _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
         return SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
 

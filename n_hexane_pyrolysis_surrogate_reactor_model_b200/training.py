@@ -1,0 +1,199 @@
+"""One CRNN training step on the GPU, batched over conditions and sharded over ranks.
+
+Mirrors SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py (and its narrow Eoff / Eon siblings):
+
+  ParameterConverter(p)            :194-228   flat p[189] -> (w_in[11,9], w_b[9], w_out[9,9]); element-balance
+                                              projection of w_out, clamps, w_in[:9] = clamp(-w_out, 0, ul)
+  Trainer.predict_n_ode(p, i_exp)  :370-385   ParameterConverter -> odeint(rtol 1e-4, atol 1e-6) -> clamp
+  Trainer.loss_n_ode(p, i_exp)     :387-396   MSE of prediction / yscale vs label / yscale over 7 species x 801 points
+  loss.backward(); clip_grad_norm_([p], 10); AdamW(lr 5e-4, wd 1e-4).step()   :414-422, :500
+
+The reference updates after every single sample (batch size 1, ~0.23 s per sample on a CPU core).  Here one step
+takes the whole local shard of conditions at once: forward trajectories and the adjoint gradient are two kernel
+launches of the C-ABI library (pfr_integrate with dense raw output, pfr_loss_grad), the tiny ParameterConverter
+and its backward run as torch autograd on 189 numbers, and the only communication is one all-reduce of
+[grad(189) | loss | count] (NCCL on GPUs, gloo in the CPU test).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .containers import CRNNParams
+from .surrogate import NS, NTOTAL, TRAINING_WIDE_CLAMPS, CrnnModel, Surrogate, _ptr, _stream
+
+NR = 9
+NPAR = 189
+E_H = (2, 4, 4, 6, 6, 8, 14, 10, 10)   # WIDE_Eoff_surrogate_model_training.py:129-130
+E_C = (0, 1, 2, 2, 3, 4, 6, 4, 5)
+
+
+@dataclass
+class ConverterSpec:
+    """Fits, clamps and slope formulas of one trainer (form 'wide' | 'eon' | 'eoff')."""
+    form: str = "wide"
+    A_fit: float = 18.42068
+    b_fit: float = 2.112
+    Ea_fit: float = 63.304
+    slope_reg: float = 0.5
+    wout: tuple = (-5.0, 5.0)
+    win: tuple = (0.0, 5.0)
+    Ea: tuple = (5.0, 200.0)
+    b: tuple = (-3.0, 3.0)
+    A: tuple = (1.0, 21.0)
+
+
+WIDE_LLNL = ConverterSpec()                                                    # WIDE_Eoff...:25-29,48-52
+NARROW = dict(wout=(-2.0, 2.0), win=(0.0, 2.0), Ea=(10.0, 200.0), b=(-3.0, 3.0), A=(3.0, 21.0))   # Eon...:51-56
+
+
+class ParameterConverter:
+    """p[189] -> (w_in, w_b, w_out), differentiable (torch autograd), float32 like the reference."""
+
+    def __init__(self, spec: ConverterSpec = WIDE_LLNL, device="cpu"):
+        self.spec = spec
+        f32 = torch.float32
+        E_ = torch.stack([torch.tensor(E_H, dtype=f32), torch.tensor(E_C, dtype=f32)], dim=1)
+        _, _, Vh = torch.linalg.svd(E_.T, full_matrices=True)                  # :132-133
+        self.E_null = Vh[E_.size(1):].T.contiguous().to(device)
+        A, b, Ea, reg = (torch.tensor(v, dtype=f32) for v in (spec.A_fit, spec.b_fit, spec.Ea_fit, spec.slope_reg))
+        if spec.form == "wide":                                                # :186-188
+            sA, sb, sE = A * (A / (A + NR)) * reg, b * ((A + b + NR) / (A + b + NR + NS)) * reg, Ea * ((Ea + A + NR) / (Ea - NR)) * reg
+        elif spec.form == "eon":                                               # Eon...:291-293
+            sA, sb, sE = A * (A / (A + NS + NR)), b * ((A + b + NR) / (A + b + NR + NS)), Ea * ((Ea + A + NS + NR) / (Ea - NS - NR))
+        elif spec.form == "eoff":                                              # Eoff...:208-210
+            sA, sb, sE = A * (A / (A + NS + NR)), b * ((A + b + NR) / (A + b + NR + NS)), Ea * ((Ea + A + b + NS + NR) / (Ea - b - NS - NR))
+        else:
+            raise ValueError(spec.form)
+        self.slope_A, self.slope_b, self.slope_Ea = (s.to(device) for s in (sA, sb, sE))
+        # projector onto the element-balance null space with the reference's 1e-4 ridge: N (N^T N + eps I)^-1 N^T
+        N = self.E_null
+        self.M = torch.linalg.solve(N.T @ N + 1e-4 * torch.eye(N.shape[1], dtype=f32, device=N.device), N.T)
+
+    def __call__(self, p: torch.Tensor):
+        s = self.spec
+        w_b = torch.abs(p[:NR]) * self.slope_A
+        w_in_b = p[NR:2 * NR] * self.slope_b
+        w_in_Ea = torch.abs(p[2 * NR:3 * NR] * self.slope_Ea)
+        w_out = p[3 * NR:(NS + 3) * NR].view(NS, NR)
+        # column-wise  E_null @ solve(N^T N + eps I, N^T w_out[:, i])  (:207-213) as one product
+        w_adj = self.E_null @ (self.M @ w_out)
+        w_adj = torch.clamp(w_adj, s.wout[0], s.wout[1])
+        w_in_only = torch.clamp(-w_adj, s.win[0], s.win[1])
+        w_in_Ea = torch.clamp(w_in_Ea, s.Ea[0], s.Ea[1])
+        w_in_b = torch.clamp(w_in_b, s.b[0], s.b[1])
+        w_b = torch.clamp(w_b, s.A[0], s.A[1])
+        w_in = torch.cat([w_in_only, w_in_Ea.unsqueeze(0), w_in_b.unsqueeze(0)], dim=0)
+        return w_in, w_b, w_adj
+
+
+@dataclass
+class TrainingBatch:
+    """Device-resident training conditions of one rank (knot-major SoA like the sweep)."""
+    T0: torch.Tensor       # [n] float32
+    c0: torch.Tensor       # [n] float32
+    tgrid: torch.Tensor    # [801, n] float32
+    Tprof: torch.Tensor | None   # [801, n] float32 (Eon trainer) or None (isothermal)
+    ref: torch.Tensor      # [801, 7, n] float32 labels, mol/m3
+    yscale: torch.Tensor   # [7, n] float32 = clamp(max_t - min_t, 1e-6, inf)  (:105)
+
+    @property
+    def n(self):
+        return self.T0.numel()
+
+    @staticmethod
+    def yscale_from_labels(ref: torch.Tensor) -> torch.Tensor:
+        return torch.clamp(ref.amax(dim=0) - ref.amin(dim=0), min=1e-6)
+
+
+def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum [grad(189) | loss | count] over the ranks (the step's only collective); identity without a process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+class CrnnTrainer:
+    """loss / gradient / optimiser step for the flat parameter vector p[189]."""
+
+    def __init__(self, batch: TrainingBatch, spec: ConverterSpec = WIDE_LLNL, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-4, atol=1e-6,
+                 substeps=2, lr=5e-4, weight_decay=1e-4, clip=10.0, group=None):
+        self.batch, self.clamps, self.rtol, self.atol, self.substeps = batch, clamps, rtol, atol, substeps
+        self.device = batch.T0.device
+        self.converter = ParameterConverter(spec)
+        self.clip, self.group = clip, group
+        self.lr, self.weight_decay = lr, weight_decay
+        self.opt = None
+        # integrate() only needs a CRNN handle; reuse Surrogate's plumbing without MLPs
+        self._sur = Surrogate.__new__(Surrogate)
+        self._sur.device = self.device
+        self._sur.energy_on = batch.Tprof is not None
+
+    # ---------------------------------------------------------------- device part
+    def forward(self, w_in, w_b, w_out):
+        """Raw knot states [801, 9, n] (float64) of the current parameters; status [n]."""
+        crnn = CrnnModel(CRNNParams(w_in, w_b, w_out), self.clamps)
+        self._sur.crnn = crnn
+        b = self.batch
+        res = self._sur.integrate(b.T0, b.c0, tgrid=b.tgrid, Tprof=b.Tprof, rtol=self.rtol, atol=self.atol, dense=True, dense_raw=True)
+        return crnn, res
+
+    def loss_grad_w(self, w_in, w_b, w_out):
+        """(sum of per-condition losses, sum of per-condition gradients [189], failed count) on this rank, float64 CUDA."""
+        b = self.batch
+        crnn, res = self.forward(w_in, w_b, w_out)
+        n = b.n
+        loss = torch.empty(n, dtype=torch.float64, device=self.device)
+        grad = torch.empty((NPAR, n), dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().pfr_loss_grad(crnn.handle, n, _ptr(b.T0), _ptr(b.tgrid), _ptr(b.Tprof), _ptr(res.dense), _ptr(b.ref),
+                                            _ptr(b.yscale), self.substeps, _ptr(loss), _ptr(grad), _stream()), "pfr_loss_grad")
+        out = torch.empty(NPAR + 1, dtype=torch.float64, device=self.device)
+        both = torch.cat([grad, loss.unsqueeze(0)], dim=0).contiguous()
+        _lib.check(_lib.lib().pfr_reduce_rows(_ptr(both), NPAR + 1, n, _ptr(out), _stream()), "pfr_reduce_rows")
+        return out[NPAR], out[:NPAR], int((res.status != 0).sum())
+
+    # ---------------------------------------------------------------- host part (189 numbers)
+    def loss_and_grad(self, p: torch.Tensor):
+        """Mean loss over all ranks' conditions and its gradient with respect to p (float32 CPU tensors)."""
+        pc = p.detach().to("cpu", torch.float32).requires_grad_(True)
+        w_in, w_b, w_out = self.converter(pc)
+        lsum, gsum, bad = self.loss_grad_w(w_in.detach().numpy(), w_b.detach().numpy(), w_out.detach().numpy())
+        packed = torch.cat([gsum, lsum.reshape(1), torch.tensor([float(self.batch.n)], dtype=torch.float64, device=self.device)])
+        packed = allreduce_packed(packed, self.group).cpu()
+        count = float(packed[NPAR + 1])
+        g = (packed[:NPAR] / count).to(torch.float32)
+        g_in, g_b, g_out = g[:99].view(11, 9), g[99:108], g[108:].view(9, 9)
+        (gp,) = torch.autograd.grad((w_in, w_b, w_out), pc, (g_in, g_b, g_out))
+        return float(packed[NPAR]) / count, gp, bad
+
+    def step(self, p: torch.Tensor):
+        """One optimiser step on p (a CPU float32 leaf tensor): gradient, clip_grad_norm_(10), AdamW(5e-4, wd 1e-4)."""
+        if self.opt is None:
+            self.opt = torch.optim.AdamW([p], lr=self.lr, weight_decay=self.weight_decay)
+        loss, gp, bad = self.loss_and_grad(p)
+        self.opt.zero_grad()
+        p.grad = gp
+        if self.clip:
+            torch.nn.utils.clip_grad_norm_([p], self.clip)
+        self.opt.step()
+        return loss, bad
+
+
+def synthetic_labels(sur: Surrogate, teacher: CRNNParams, T, P, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-10, atol=1e-12) -> TrainingBatch:
+    """Training batch with teacher-generated labels (the reference's Cantera label files are not shipped): time grid
+    from the surrogate's time MLP at (T, P, 1.0 m, 2.5 m/s), isothermal, labels = teacher CRNN trajectories at the knots."""
+    T = torch.as_tensor(np.asarray(T, np.float32)).to(sur.device)
+    P = torch.as_tensor(np.asarray(P, np.float32)).to(sur.device)
+    c0 = sur.inlet_concentration(T, P)
+    tgrid, _ = sur.time_grid(T, P, None, None)
+    helper = Surrogate.__new__(Surrogate)
+    helper.device = sur.device
+    helper.crnn = CrnnModel(teacher, clamps)
+    res = helper.integrate(T, c0, tgrid=tgrid, rtol=rtol, atol=atol, dense=True).raise_on_failure()
+    ref = res.dense[:, :7, :].to(torch.float32).contiguous()
+    return TrainingBatch(T, c0, tgrid, None, ref, TrainingBatch.yscale_from_labels(ref).contiguous())

@@ -88,6 +88,30 @@ def truth_batch(tgrid, Tprof, u0, w_in, w_b, w_out, inter=(-30.0, 30.0), upto=No
     return y, yk
 
 
+def truth_knots_dp(tgrid, Tprof, u0, w_in, w_b, w_out, inter=(-30.0, 30.0), rtol=1e-13, atol=1e-16, nthreads=0):
+    """Converged knot states [N,801,9] for DOUBLE parameters (finite differences of the training loss)."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    tgrid, Tprof, u0 = f(tgrid), f(Tprof), f(u0)
+    w_in, w_b, w_out = d(w_in), d(w_b), d(w_out)
+    N = tgrid.shape[0]
+    y = np.zeros((N, 9), np.float64)
+    yk = np.zeros((N, 801, 9), np.float64)
+    F, D, I = ctypes.c_float, ctypes.c_double, ctypes.c_int
+    bad = lib().oracle_truth_batch_dp(I(N), _p(tgrid, F), _p(Tprof, F), _p(u0, F), _p(w_in, D), _p(w_b, D), _p(w_out, D),
+                                      D(inter[0]), D(inter[1]), None, D(rtol), D(atol), _p(y, D), _p(yk, D), I(nthreads))
+    if bad:
+        raise RuntimeError(f"oracle_truth_batch_dp: {bad} interval(s) failed")
+    return yk
+
+
+def training_loss(yk, ref, yscale, lb=1e-6, ub=60.0):
+    """Per-condition loss_n_ode from knot states yk[N,801,9], labels ref[N,801,7], yscale[N,7] (WIDE_Eoff...:387-396)."""
+    pred = np.clip(yk[:, :, :7], lb, ub)
+    d = (pred - ref) / yscale[:, None, :]
+    return np.mean(d * d, axis=(1, 2))
+
+
 def rhs_batch(T, u, w_in, w_b, w_out, inter=(-30.0, 30.0)):
     T = np.ascontiguousarray(T, np.float64)
     u = np.ascontiguousarray(u, np.float64)

@@ -230,6 +230,21 @@ int oracle_truth_batch(int N, const float *tgrid, const float *Tprof, const floa
     return bad;
 }
 
+/* Same as oracle_truth_batch with DOUBLE parameters (finite-difference checks of the training gradient) */
+int oracle_truth_batch_dp(int N, const float *tgrid, const float *Tprof, const float *u0, const double *w_in,
+                          const double *w_b, const double *w_out, double inter_lo, double inter_hi, const int *upto,
+                          double rtol, double atol, double *y_out, double *y_knots, int nthreads) {
+    truth_par p;
+    for (int i = 0; i < 99; i++) p.w_in[i] = w_in[i];
+    for (int i = 0; i < 9; i++) p.w_b[i] = w_b[i];
+    for (int i = 0; i < 81; i++) p.w_out[i] = w_out[i];
+    p.lo = inter_lo; p.hi = inter_hi;
+    int bad = 0;
+    tr_args a = {tgrid, Tprof, u0, &p, upto, rtol, atol, y_out, y_knots, &bad};
+    parallel_for(N, nthreads, tr_body, &a);
+    return bad;
+}
+
 /* Batched RHS in double at given temperatures (a7 without the knot lookup): du[N][9] */
 void oracle_rhs_batch(int N, const double *T, const double *u, const float *w_in, const float *w_b, const float *w_out,
                       double inter_lo, double inter_hi, double *du) {

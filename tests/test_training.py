@@ -1,0 +1,133 @@
+"""Training step (config 5): ParameterConverter, loss and adjoint gradient, optimiser step."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, cond4, packed_path, rel_err
+
+
+# ----------------------------------------------------------------------------------------------- CPU
+def test_product_converter_reproduces_reference_known_answers():
+    """The product's ParameterConverter (one projector product instead of nine solves) on the reference's stored
+    updated_p -> final_parameters pairs, and against the oracle's literal restatement."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import NARROW, ConverterSpec, ParameterConverter
+    from oracle import reference_path as R
+    kat = np.load(f"{GOLDEN}/converter_kat.npz")
+    for name, spec, ospec in (("LLNL_Eoff_wide", ConverterSpec(), R.ConverterSpec()),
+                              ("NUIG_Eon", ConverterSpec(form="eon", b_fit=1.858, Ea_fit=58.397, **NARROW), R.narrow_spec("eon", 1.858, 58.397))):
+        p = torch.tensor(kat[f"{name}/updated_p"])
+        w_in, w_b, w_out = ParameterConverter(spec)(p)
+        assert np.max(np.abs(w_in.numpy() - kat[f"{name}/w_in"])) < 3e-6
+        assert np.array_equal(w_b.numpy(), kat[f"{name}/w_b"])
+        assert np.max(np.abs(w_out.numpy() - kat[f"{name}/w_out"])) < 3e-6
+        o_in, o_b, o_out = R.parameter_converter(p, ospec)
+        assert torch.allclose(w_in, o_in, atol=3e-6) and torch.allclose(w_out, o_out, atol=3e-6) and torch.equal(w_b, o_b)
+
+
+def test_converter_gradient_has_the_reference_dead_slice():
+    """p[108:189] never reaches the outputs (overwritten by clamp(-w_out), WIDE_Eoff...:200,221): zero gradient."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import ParameterConverter
+    p = (torch.rand(189) * 0.8 + 0.2).requires_grad_(True)
+    w_in, w_b, w_out = ParameterConverter()(p)
+    (w_in.sum() + w_b.sum() + (w_out ** 2).sum()).backward()
+    assert torch.all(p.grad[108:] == 0) and torch.any(p.grad[:108] != 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ar_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import allreduce_packed
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    packed = torch.cat([torch.full((189,), float(rank + 1), dtype=torch.float64), torch.tensor([0.5 * (rank + 1), 320.0], dtype=torch.float64)])
+    out = allreduce_packed(packed)
+    ret[rank] = bool(torch.all(out[:189] == 3.0)) and float(out[189]) == 1.5 and float(out[190]) == 640.0
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_ar_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert all(ret[r] for r in range(2))
+
+
+# ----------------------------------------------------------------------------------------------- GPU
+def _setup(surrogates, model_sets, conditions, n=12):
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import CrnnTrainer, synthetic_labels
+    a = conditions["training_wide_2D"]
+    sel = np.linspace(0, len(a) - 1, n).astype(int)
+    T, P = a[sel, 0].astype(np.float32), (a[sel, 1] * 1e5).astype(np.float32)
+    sur = surrogates("LLNL", "Eoff")
+    teacher = model_sets("LLNL", "Eoff", "Eoff_wide").crnn
+    batch = synthetic_labels(sur, teacher, T, P)
+    return CrnnTrainer(batch), batch, T, P
+
+
+@pytest.mark.gpu
+def test_loss_and_gradient_vs_oracle_finite_differences(surrogates, model_sets, conditions):
+    """Student = the stored LLNL_Eoff_wide_v2 parameters, labels from the LLNL_Eoff_wide teacher, training RHS clamps
+    (exponent +-10).  The GPU loss equals the oracle's (converged knot states -> numpy loss) to 1e-7 relative with the
+    forward pass at 1e-10, and the adjoint gradient matches central finite differences of the oracle loss taken in
+    float64 parameters to 2e-4 of the gradient's scale (RK4 adjoint, 2 sub-steps per knot interval)."""
+    from oracle import c_oracle as CO
+    tr, batch, T, P = _setup(surrogates, model_sets, conditions)
+    tr.rtol, tr.atol = 1e-10, 1e-12
+    student = model_sets("LLNL", "Eoff").crnn
+    lsum, gsum, bad = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
+    assert bad == 0
+    n = batch.n
+    tg = batch.tgrid.cpu().numpy().T.copy()
+    Tp = np.repeat(T[:, None], 801, 1)
+    c0 = np.zeros((n, 9), np.float32)
+    c0[:, 6] = batch.c0.cpu().numpy()
+    ref = batch.ref.cpu().numpy().transpose(2, 0, 1).astype(np.float64)      # [n, 801, 7]
+    ysc = batch.yscale.cpu().numpy().T.astype(np.float64)                     # [n, 7]
+
+    def oracle_loss(w_in, w_b, w_out):
+        yk = CO.truth_knots_dp(tg, Tp, c0, w_in, w_b, w_out, inter=(-10.0, 10.0), nthreads=8)
+        return CO.training_loss(yk, ref, ysc).sum()
+
+    w = [student.w_in.astype(np.float64), student.w_b.astype(np.float64), student.w_out.astype(np.float64)]
+    L0 = oracle_loss(*w)
+    assert abs(float(lsum) - L0) / L0 < 1e-7
+    g = gsum.cpu().numpy()
+    g_in, g_b, g_out = g[:99].reshape(11, 9), g[99:108], g[108:].reshape(9, 9)
+    scale = np.abs(g).max()
+    checks = [(0, (6, 0)), (0, (0, 2)), (0, (9, 0)), (0, (9, 4)), (0, (10, 0)), (0, (10, 6)), (1, (0,)), (1, (3,)), (2, (6, 0)),
+              (2, (2, 0)), (2, (0, 4)), (2, (8, 8))]
+    for which, idx in checks:
+        h = 1e-6 * max(1.0, abs(w[which][idx]))
+        wp = [a.copy() for a in w]
+        wm = [a.copy() for a in w]
+        wp[which][idx] += h
+        wm[which][idx] -= h
+        fd = (oracle_loss(*wp) - oracle_loss(*wm)) / (2 * h)
+        got = (g_in, g_b, g_out)[which][idx]
+        assert abs(got - fd) < 2e-4 * scale + 1e-6 * abs(fd), (which, idx, got, fd)
+
+
+@pytest.mark.gpu
+def test_training_steps_reduce_the_loss(surrogates, model_sets, conditions):
+    """A few reference-style steps (clip 10, AdamW 5e-4, wd 1e-4) from the stored updated_p perturbed with N(0, 0.05^2)
+    noise (SURVEY config 5): the loss goes down and no trajectory fails."""
+    kat = np.load(f"{GOLDEN}/converter_kat.npz")
+    tr, batch, T, P = _setup(surrogates, model_sets, conditions, n=32)
+    g = torch.Generator().manual_seed(0)
+    p = (torch.tensor(kat["LLNL_Eoff_wide/updated_p"]) + 0.05 * torch.randn(189, generator=g)).requires_grad_(True)
+    losses = []
+    for _ in range(6):
+        loss, bad = tr.step(p)
+        assert bad == 0 and np.isfinite(loss)
+        losses.append(loss)
+    assert losses[-1] < losses[0]
