@@ -188,6 +188,7 @@ def run_ours(args):
         del sur
         torch.cuda.empty_cache()
 
+    variants["train_step_WIDE_Eoff"] = training_variant(dev, world, rank, time_steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -222,6 +223,32 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def training_variant(dev, world, rank, time_steps):
+    """Config 5: one CRNN training step (batched forward + adjoint gradient + 189-float all-reduce + clip + AdamW) over the 640
+    training conditions of sampling_case_wide_2D.csv (train_test_split seed 42 is immaterial to the timing: the first 640 rows),
+    sharded over the ranks; teacher-generated labels (the reference's Cantera labels are not shipped)."""
+    import torch
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import Surrogate
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import shard_bounds
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import CrnnTrainer, synthetic_labels
+
+    gold = os.path.join(ROOT, "tests", "golden")
+    a = np.load(os.path.join(gold, "conditions.npz"))["training_wide_2D"][:640]
+    lo, hi = shard_bounds(len(a), world, rank)
+    sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), "Eoff"), device=dev)
+    teacher = ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), "Eoff", "Eoff_wide").crnn
+    batch = synthetic_labels(sur, teacher, a[lo:hi, 0].astype(np.float32), (a[lo:hi, 1] * 1e5).astype(np.float32))
+    tr = CrnnTrainer(batch)
+    kat = np.load(os.path.join(gold, "converter_kat.npz"))
+    p = (torch.tensor(kat["LLNL_Eoff_wide/updated_p"]) + 0.05 * torch.randn(189, generator=torch.Generator().manual_seed(0))).requires_grad_(True)
+    losses = []
+    ms, _, launches = time_steps(lambda: losses.append(tr.step(p)[0]), 5, 3)
+    return {"value": len(a) * 5 / (ms * 1e-3), "unit": "training samples/s", "ms_per_step": ms / 5, "conditions": len(a),
+            "kernel_launches_per_step": launches / 5, "loss_first": losses[0], "loss_last": losses[-1],
+            "reference": "WIDE_Eoff_surrogate_model_training.py: ~0.225 s per sample per CPU core (SURVEY 6), batch size 1"}
 
 
 def cpu_baseline(args, variant="Eon", sample=None):

@@ -259,30 +259,31 @@ def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6,
         stats.nfe += 1
         return func(tt, y)
 
-    # _before_integrate + _select_initial_step(order = 5 - 1)
+    # _before_integrate + _select_initial_step(order = 5 - 1); torchdiffeq decorates _select_initial_step,
+    # _compute_error_ratio and _optimal_step_size with @torch.no_grad(): step sizes carry no gradient
     f0 = f(t[0], y0)
-    scale = atol + torch.abs(y0) * rtol
-    d0 = _rms(y0 / scale)
-    d1 = _rms(f0 / scale)
-    if d0 < 1e-5 or d1 < 1e-5:
-        h0 = torch.tensor(1e-6, dtype=sd)
-    else:
-        h0 = 0.01 * d0 / d1
-    h0 = h0.abs()
-    y1 = y0 + h0 * f0
-    f1 = f(t[0] + h0, y1)
-    d2 = torch.abs(_rms((f1 - f0) / scale) / h0)
-    if d1 <= 1e-15 and d2 <= 1e-15:
-        h1 = torch.max(torch.tensor(1e-6, dtype=sd), h0 * 1e-3)
-    else:
-        h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
-    h1 = h1.abs()
-    dt = torch.min(100 * h0, h1).to(torch.float64)
+    with torch.no_grad():
+        scale = atol + torch.abs(y0) * rtol
+        d0 = _rms(y0 / scale)
+        d1 = _rms(f0 / scale)
+        if d0 < 1e-5 or d1 < 1e-5:
+            h0 = torch.tensor(1e-6, dtype=sd)
+        else:
+            h0 = 0.01 * d0 / d1
+        h0 = h0.abs()
+        y1 = y0 + h0 * f0
+        f1 = f(t[0] + h0, y1)
+        d2 = torch.abs(_rms((f1 - f0) / scale) / h0)
+        if d1 <= 1e-15 and d2 <= 1e-15:
+            h1 = torch.max(torch.tensor(1e-6, dtype=sd), h0 * 1e-3)
+        else:
+            h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+        h1 = h1.abs()
+        dt = torch.min(100 * h0, h1).to(torch.float64)
 
     rk_y, rk_f, rk_t0, rk_t1 = y0, f0, t[0], t[0]
     interp = [y0] * 5
-    sol = torch.empty(len(t), *y0.shape, dtype=sd)
-    sol[0] = y0
+    sols = [y0]
     for i in range(1, len(t)):
         next_t = t[i]
         n_steps = 0
@@ -295,20 +296,24 @@ def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6,
             assert torch.isfinite(ya).all(), "non-finite values in state `y`"
             # ---- _runge_kutta_step ----
             t0s, dts, t1s = ta.to(sd), dt.to(sd), tb.to(sd)
-            k = torch.empty(*fa.shape, 7, dtype=sd)
-            k[..., 0] = fa
+            # k is kept as a list of stage derivatives and stacked for the weighted sums: the same arithmetic as
+            # torchdiffeq's pre-allocated k[..., i] buffer, but differentiable (no in-place writes into saved tensors)
+            ks = [fa]
             for j, (al, be) in enumerate(zip(alpha, beta)):
                 if float(al) == 1.0:
                     ti, prev = t1s, True
                 else:
                     ti, prev = t0s + al * dts, False
-                yi = ya + torch.sum(k[..., : j + 1] * (be * dts), dim=-1).view_as(fa)
-                k[..., j + 1] = f(ti, yi, prev)
+                kj = torch.stack(ks, dim=-1)
+                yi = ya + torch.sum(kj * (be * dts), dim=-1).view_as(fa)
+                ks.append(f(ti, yi, prev))
+            k = torch.stack(ks, dim=-1)
             yb = yi
             fb = k[..., -1]
             err = torch.sum(k * (dts * c_err), dim=-1)
-            tol = atol + rtol * torch.max(ya.abs(), yb.abs())
-            ratio = _rms(err / tol).abs()
+            with torch.no_grad():
+                tol = atol + rtol * torch.max(ya.abs(), yb.abs())
+                ratio = _rms(err / tol).abs()
             accept = bool(ratio <= 1)
             if accept:
                 dtt = dt.to(sd)
@@ -342,8 +347,8 @@ def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6,
         for coef in interp[2:]:
             xp = xp * x
             total = total + xp * coef
-        sol[i] = total
-    return sol
+        sols.append(total)
+    return torch.stack(sols, dim=0)
 
 
 # ---------------------------------------------------------------------------------------------
