@@ -32,13 +32,43 @@ constexpr int COOP_PER_BLOCK = COOP_PER_WARP * (COOP_BLOCK / 32);
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 
+constexpr int PADN = 10;  // 9-vectors padded to 10 so that rows stay 16-byte aligned in shared memory
+// Tuning switches, all measured on B200 at 2^18 LLNL Eon conditions (shipped setting first, 88.8 ms):
+//   PFR_OPAQUE_PTR 0 volatile scalar parameter loads | 1 plain loads through an opaque pointer: the compiler merges /
+//                    hoists them again and spills ~1 KB per thread
+//   PFR_VECLD      0 coefficient read inside the FMA chain | 1 vector loads (spills) | 2 nine scalar loads first (no change)
+//   PFR_DOT2       0 one accumulator per dot product | 1 two (no change)
+//   PFR_AINV_SMEM  0 inverse stays in registers | 1 parked in shared memory (LSU-bound, 99 ms)
+#ifndef PFR_OPAQUE_PTR
+#define PFR_OPAQUE_PTR 0
+#endif
+#ifndef PFR_VECLD
+#define PFR_VECLD 0
+#endif
+
+// Block-shared copy of the CRNN parameters, re-laid out per lane: lane l, slot m owns reaction / species 3m+l and
+// reads its nine coefficients as one contiguous row.
 template <typename real>
-struct CoopParams {  // block-shared copy of the CRNN parameters: lanes of a group read different columns / rows
-    real nu[NS * NR];
-    real wout[NS * NR];
+struct CoopParams {
+    real nuL[3][3][PADN];    // nuL[l][m][k]   = nu[k][3m+l]
+    real woutL[3][3][PADN];  // woutL[l][m][j] = wout[3m+l][j]
     real Ea[NR], b[NR], lnA[NR];
     FastTables ft;  // log / exp tables (used by the double instantiation)
 };
+
+// Nine consecutive reals (a 16-byte aligned row) with vector loads
+__device__ __forceinline__ void lds9(const double* q, double (&v)[NS]) {
+    const double2* q2 = reinterpret_cast<const double2*>(q);
+#pragma unroll
+    for (int e = 0; e < 4; e++) { const double2 t = q2[e]; v[2 * e] = t.x; v[2 * e + 1] = t.y; }
+    v[8] = q[8];
+}
+__device__ __forceinline__ void lds9(const float* q, float (&v)[NS]) {
+    const float2* q2 = reinterpret_cast<const float2*>(q);
+#pragma unroll
+    for (int e = 0; e < 4; e++) { const float2 t = q2[e]; v[2 * e] = t.x; v[2 * e + 1] = t.y; }
+    v[8] = q[8];
+}
 
 // log / exp of the hot loop: table-driven in double (fastmath.cuh), CUDA's logf / expf in float
 template <typename real> __device__ __forceinline__ real c_log(real x, const CoopParams<real>& sp);
@@ -51,7 +81,13 @@ template <> __device__ __forceinline__ float c_exp<float>(float x, const CoopPar
 // Parameter reads from the block-shared copy.  volatile: the values are loop-invariant, and without it the
 // compiler hoists all 54 of a lane's coefficients out of the step loop into registers (and then spills).
 template <typename real>
-__device__ __forceinline__ real ldp(const real* q) { return *reinterpret_cast<const volatile real*>(q); }
+__device__ __forceinline__ real ldp(const real* q) {
+#if PFR_OPAQUE_PTR
+    return *q;
+#else
+    return *reinterpret_cast<const volatile real*>(q);
+#endif
+}
 
 template <typename real>
 __device__ __forceinline__ void gather9(const real (&own)[3], real (&all)[NS], int base) {
@@ -80,9 +116,24 @@ template <> __device__ __forceinline__ double fast_rcp<double>(double x) {
     return fma(r, e, r);
 }
 
+// The parameter block is loop-invariant and read by every RHS evaluation.  Re-deriving its address from an opaque
+// zero keeps the compiler from merging the reads of different evaluations (which would pin a lane's 54
+// coefficients in registers for the whole step) while leaving it free to schedule / vectorise them inside one.
+template <typename real>
+__device__ __forceinline__ const CoopParams<real>& opaque(const CoopParams<real>& sp) {
+#if PFR_OPAQUE_PTR
+    unsigned z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+    return *reinterpret_cast<const CoopParams<real>*>(reinterpret_cast<const char*>(&sp) + z);
+#else
+    return sp;
+#endif
+}
+
 template <typename real, bool WithDeriv>
-__device__ __forceinline__ void coop_arrhenius(const CoopParams<real>& sp, real inv_R, int l, real T, real (&kT)[3], real& mE_out,
+__device__ __forceinline__ void coop_arrhenius(const CoopParams<real>& sp_, real inv_R, int l, real T, real (&kT)[3], real& mE_out,
                                                real& invT_out) {
+    const CoopParams<real>& sp = opaque(sp_);
     const real invT = fast_rcp<real>(T);
     const real mE = -inv_R * invT;
     const real lnT = c_log<real>(T, sp);
@@ -114,9 +165,10 @@ __device__ __forceinline__ void coop_arrhenius(const CoopParams<real>& sp, real 
 // du_own = f(y) for the lane's three species.  KeepJac also returns g (masked rates, all nine) and q for the
 // lane's species.
 template <typename real, bool KeepJac>
-__device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnParams<real>& p, int l, int base,
+__device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp_, const CrnnParams<real>& p, int l, int base,
                                          const real (&kT)[3], const real (&yin)[3], real (&du)[3], real (&g_all)[NS],
                                          real (&q_own)[3]) {
+    const CoopParams<real>& sp = opaque(sp_);
     real lnY[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {
@@ -129,9 +181,19 @@ __device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnP
     real r[3], gm[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {
-        const int j = 3 * m + l;
         real z;
-#define A_(k) ldp(&sp.nu[(k) * NR + j])
+#if PFR_VECLD == 2
+        real c9[NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) c9[k] = *reinterpret_cast<const volatile real*>(&sp.nuL[l][m][k]);
+#define A_(k) c9[k]
+#elif PFR_VECLD
+        real c9[NS];
+        lds9(sp.nuL[l][m], c9);
+#define A_(k) c9[k]
+#else
+#define A_(k) ldp(&sp.nuL[l][m][k])
+#endif
 #define B_(k) lnY_all[k]
         PFR_DOT9(z, kT[m], A_, B_);
 #undef A_
@@ -144,9 +206,19 @@ __device__ __forceinline__ void coop_rhs(const CoopParams<real>& sp, const CrnnP
     if (KeepJac) gather9<real>(gm, g_all, base);
 #pragma unroll
     for (int m = 0; m < 3; m++) {
-        const int i = 3 * m + l;
         real s;
-#define A_(j) ldp(&sp.wout[i * NR + (j)])
+#if PFR_VECLD == 2
+        real c9[NS];
+#pragma unroll
+        for (int j = 0; j < NR; j++) c9[j] = *reinterpret_cast<const volatile real*>(&sp.woutL[l][m][j]);
+#define A_(j) c9[j]
+#elif PFR_VECLD
+        real c9[NS];
+        lds9(sp.woutL[l][m], c9);
+#define A_(j) c9[j]
+#else
+#define A_(j) ldp(&sp.woutL[l][m][j])
+#endif
 #define B_(j) r_all[j]
         PFR_DOT9(s, real(0), A_, B_);
 #undef A_
@@ -181,25 +253,27 @@ __global__ void __launch_bounds__(COOP_BLOCK, PFR_COOP_MINB)
 rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     using namespace rodas4;
     static_assert(!kRamp || kKnots, "a temperature ramp needs knot-limited stepping");
-    __shared__ CoopParams<real> sp;
+    __shared__ __align__(16) CoopParams<real> sp_block;
+    CoopParams<real>& sp0 = sp_block;
 #if PFR_AINV_SMEM
     extern __shared__ __align__(16) unsigned char coop_dyn[];  // [27][COOP_BLOCK] reals: each lane's rows of E^-1
     real* const Ainv = reinterpret_cast<real*>(coop_dyn) + threadIdx.x;
 #else
     real* const Ainv = nullptr;
 #endif
-    for (int e = threadIdx.x; e < NS * NR; e += COOP_BLOCK) {
-        sp.nu[e] = p.nu[e / NR][e % NR];
-        sp.wout[e] = p.wout[e / NR][e % NR];
+    for (int e = threadIdx.x; e < 3 * 3 * PADN; e += COOP_BLOCK) {
+        const int ll = e / (3 * PADN), mm = (e / PADN) % 3, kk = e % PADN;
+        sp0.nuL[ll][mm][kk] = kk < NS ? p.nu[kk][3 * mm + ll] : real(0);
+        sp0.woutL[ll][mm][kk] = kk < NS ? p.wout[3 * mm + ll][kk] : real(0);
     }
     if (threadIdx.x < NR) {
-        sp.Ea[threadIdx.x] = p.Ea[threadIdx.x];
-        sp.b[threadIdx.x] = p.b[threadIdx.x];
-        sp.lnA[threadIdx.x] = p.lnA[threadIdx.x];
+        sp0.Ea[threadIdx.x] = p.Ea[threadIdx.x];
+        sp0.b[threadIdx.x] = p.b[threadIdx.x];
+        sp0.lnA[threadIdx.x] = p.lnA[threadIdx.x];
     }
     if (sizeof(real) == 8) {
-        for (int e = threadIdx.x; e < LOGTAB_N; e += COOP_BLOCK) sp.ft.logtab[e] = a.tables->logtab[e];
-        for (int e = threadIdx.x; e < EXPTAB_N; e += COOP_BLOCK) sp.ft.exptab[e] = a.tables->exptab[e];
+        for (int e = threadIdx.x; e < LOGTAB_N; e += COOP_BLOCK) sp0.ft.logtab[e] = a.tables->logtab[e];
+        for (int e = threadIdx.x; e < EXPTAB_N; e += COOP_BLOCK) sp0.ft.exptab[e] = a.tables->exptab[e];
     }
     __syncthreads();
 
@@ -238,7 +312,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
         slope = (real(a.Tprof[n + i]) - Tk) / real(tk1 - tk);
     }
     real kT[3], mE, invT;
-    if (!kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk, kT, mE, invT);
+    if (!kRamp) coop_arrhenius<real, false>(sp0, p.inv_R, l, Tk, kT, mE, invT);
 
     const real rtol = real(a.rtol), atol = real(a.atol);
     int nacc = 0, nrej = 0, nrhs = 0, status = 0;
@@ -247,6 +321,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
     bool done = (kend == 0) || !(t_final > t);
 
     while (__any_sync(FULL, !done)) {
+        const CoopParams<real>& sp = opaque(sp_block);
         // ---------------- f0, df/dt, Jacobian rows at (t, y) ----------------
         real ak1[3], fx[3], A[3][NS];
         real g_all[NS], q_own[3];
@@ -281,7 +356,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             for (int m = 0; m < 3; m++) {
                 real s = real(0);
 #pragma unroll
-                for (int j = 0; j < NR; j++) s = fma(ldp(&sp.wout[(3 * m + l) * NR + j]), gd[j], s);
+                for (int j = 0; j < NR; j++) s = fma(ldp(&sp.woutL[l][m][j]), gd[j], s);
                 fx[m] = s * slope;
                 ak1[m] = fma(h * real(d1), fx[m], ak1[m]);
             }
@@ -293,7 +368,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             for (int m = 0; m < 3; m++) {
                 real G[NR];
 #pragma unroll
-                for (int j = 0; j < NR; j++) G[j] = ldp(&sp.wout[(3 * m + l) * NR + j]) * g_all[j];
+                for (int j = 0; j < NR; j++) G[j] = ldp(&sp.woutL[l][m][j]) * g_all[j];
 #pragma unroll
                 for (int k = 0; k < NS; k++) {
                     real s = real(0);
