@@ -184,6 +184,47 @@ class CrnnTrainer:
         return loss, bad
 
 
+def save_history(path: str, history: dict, final: tuple | None = None, p: torch.Tensor | None = None) -> None:
+    """np.savez(save_path, **history) as the reference writes it (WIDE_Eoff...:445-471): keys train_loss, valid_loss,
+    parameters (object array of {'w_in','w_b','w_out'} float32 dicts) and, at the end of training, final_parameters and
+    updated_p.  The files load with the reference's load_npz_parameters (parameters[-1])."""
+    data = dict(history)
+    if final is not None:
+        data["final_parameters"] = {"w_in": final[0], "w_b": final[1], "w_out": final[2]}
+    if p is not None:
+        data["updated_p"] = p.detach().cpu().numpy()
+    np.savez(path, **data)
+
+
+def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrainer | None" = None, save_path: str | None = None,
+          steps_per_epoch: int = 1, log=None) -> dict:
+    """Trainer.train (WIDE_Eoff...:398-476) with batched steps: per epoch `steps_per_epoch` optimiser steps, the validation
+    loss, ReduceLROnPlateau(mode min, factor 0.8, patience 5, threshold 1e-4 rel; :501), the history append and the
+    per-epoch np.savez.  Returns the history dict."""
+    history = {"train_loss": [], "valid_loss": [], "parameters": []}
+    sched = None
+    for epoch in range(epochs):
+        losses = [trainer.step(p)[0] for _ in range(steps_per_epoch)]
+        if sched is None:
+            sched = torch.optim.lr_scheduler.ReduceLROnPlateau(trainer.opt, mode="min", factor=0.8, patience=5, threshold=1e-4,
+                                                               threshold_mode="rel")
+        history["train_loss"].append(float(np.mean(losses)))
+        with torch.no_grad():
+            vloss = (valid or trainer).loss_and_grad(p)[0]
+        sched.step(vloss)
+        history["valid_loss"].append(float(vloss))
+        w_in, w_b, w_out = (x.detach().cpu().numpy() for x in trainer.converter(p.detach()))
+        history["parameters"].append({"w_in": w_in, "w_b": w_b, "w_out": w_out})
+        if log:
+            log(epoch, history["train_loss"][-1], vloss, trainer.opt.param_groups[0]["lr"])
+        if save_path:
+            save_history(save_path, history)
+    if save_path:
+        w = tuple(x.detach().cpu().numpy() for x in trainer.converter(p.detach()))
+        save_history(save_path, history, final=w, p=p)
+    return history
+
+
 def synthetic_labels(sur: Surrogate, teacher: CRNNParams, T, P, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-10, atol=1e-12) -> TrainingBatch:
     """Training batch with teacher-generated labels (the reference's Cantera label files are not shipped): time grid
     from the surrogate's time MLP at (T, P, 1.0 m, 2.5 m/s), isothermal, labels = teacher CRNN trajectories at the knots."""

@@ -487,3 +487,27 @@ def loss_n_ode(pred: torch.Tensor, ref: torch.Tensor, yscale: torch.Tensor) -> t
     """mse(pred[0:7]/yscale, ref[0:7]/yscale) (WIDE_Eoff…:387-396). pred/ref [9,801], yscale [9]."""
     s = yscale[:7].unsqueeze(1)
     return torch.nn.functional.mse_loss(pred[:7] / s, ref[:7] / s)
+
+
+# ---------------------------------------------------------------------------------------------
+# accuracy metrics of the sweep drivers, loop for loop (...Eoff_single_model.py:411-461, ...Eon_single_model.py:419-447)
+# ---------------------------------------------------------------------------------------------
+def accuracy_metrics(pred_sp, true_sp, absolute_denominator: bool):
+    """One species: pred/true 1-D arrays INCLUDING t = 0.  Returns the 8 numbers of one CSV row."""
+    epsilon_rel = 1.0e-5
+    true = np.asarray(true_sp)[1:]
+    pred = np.asarray(pred_sp)[1:]
+    true_final, pred_final = true[-1], pred[-1]
+    rmse_final = np.sqrt((pred_final - true_final) ** 2)
+    nrmse_final = rmse_final / (np.max(true) - np.min(true) + epsilon_rel)
+    if absolute_denominator:
+        rel_final = np.abs(pred_final - true_final) / (np.abs(true_final) + epsilon_rel) * 100
+        rel_time = np.mean(np.abs(pred - true) / (np.abs(true) + epsilon_rel)) * 100
+    else:
+        rel_final = np.abs(pred_final - true_final) / (true_final + epsilon_rel) * 100
+        rel_time = np.mean(np.abs(pred - true) / (true + epsilon_rel)) * 100
+    rmse_time = np.sqrt(np.mean((pred - true) ** 2))
+    nrmse_time = rmse_time / (np.max(true) - np.min(true) + epsilon_rel)
+    fcd = np.sqrt((np.mean(true) - np.mean(pred)) ** 2 + (np.std(true) - np.std(pred)) ** 2)
+    max_norm = np.max(np.abs(pred - true)) / (np.max(np.abs(true)) + epsilon_rel)
+    return [rmse_final, nrmse_final, rel_final, rmse_time, nrmse_time, rel_time, fcd, max_norm]

@@ -373,6 +373,61 @@ def test_sweep_sorted_equals_unsorted(surrogates, conditions):
     assert torch.equal(a.y, b.y)                                # the permutation only reorders threads
 
 
+@pytest.mark.parametrize("method,precision", [("rodas4", 64), ("rodas4", 32), ("rodas4_tpc", 64), ("dopri5", 32)])
+def test_integrators_ragged_batch_sizes(surrogates, conditions, method, precision):
+    """Batches that do not fill a warp / a 10-condition group / a CTA: every condition is an independent problem, so
+    the first n columns of a full-batch run and an n-condition run are bit-identical (Eon grids, outlet at idx_cut)."""
+    T, P, L, U = cond4(conditions)
+    s = surrogates("LLNL", "Eon")
+    full = s.sweep(T, P, L, U, method=method, precision=precision, sort=False, keep_grids=True)
+    for n in (1, 2, 9, 10, 11, 39, 40, 41, 127, 129):
+        sub = s.integrate(T[:n], s.inlet_concentration(T[:n], P[:n]), tgrid=full.tgrid[:, :n].contiguous(),
+                          Tprof=full.Tprof[:, :n].contiguous(), idx_end=full.idx_cut[:n].contiguous(), method=method,
+                          precision=precision)
+        assert torch.equal(sub.y, full.y[:, :n]) and torch.equal(sub.status, full.status[:n])
+        assert torch.equal(sub.stats, full.stats[:, :n])
+
+
+@pytest.mark.parametrize("mech,variant", [("LLNL", "Eon"), ("JetSurf", "Eoff")])
+def test_full_size_sweep_properties(surrogates, model_sets, mech, variant):
+    """BASELINE's full size (2^20 Latin-hypercube conditions on one GPU) through size-independent properties:
+    every trajectory succeeds; outlets stay inside the clamp interval; carbon and hydrogen are conserved (these
+    float32 parameter sets satisfy E^T w_out = 0 to 1e-6..3e-6, which bounds the drift of sum_i E_i y_i by that residual
+    times the integrated rates: measured <= 1.5e-3 of the inlet carbon, asserted 5e-3);
+    conversion increases with temperature on average; and 256 randomly chosen conditions match the converged
+    oracle solution on the GPU's own grids to 1e-6."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import lhs_conditions
+    from oracle import c_oracle as CO
+    from oracle import reference_path as R
+    n = 1 << 20
+    T, P, L, U = lhs_conditions(n, seed=13895)
+    s = surrogates(mech, variant)
+    res = s.sweep(T, P, L, U, rtol=1e-6, atol=1e-6)
+    assert int((res.status != 0).sum()) == 0
+    y = res.y
+    assert float(y.min()) >= 1e-6 and float(y.max()) <= 60.0
+    c0 = s.inlet_concentration(T, P).double()
+    EH = torch.tensor([2, 4, 4, 6, 6, 8, 14, 10, 10], dtype=torch.float64, device=y.device)
+    EC = torch.tensor([0, 1, 2, 2, 3, 4, 6, 4, 5], dtype=torch.float64, device=y.device)
+    assert float(((EC @ y) / (6 * c0) - 1).abs().max()) < 5e-3
+    assert float(((EH @ y) / (14 * c0) - 1).abs().max()) < 5e-3
+    conv = 1 - y[6] / c0
+    Td = torch.as_tensor(T, device=y.device)
+    assert float(conv[Td > 1100].mean()) > float(conv[Td < 920].mean()) + 0.3
+    # spot-check against the oracle at tight tolerance on the same grids
+    rng = np.random.default_rng(5)
+    sel = np.sort(rng.choice(n, 256, replace=False))
+    sub = s.sweep(T[sel], P[sel], L[sel], U[sel], rtol=1e-9, atol=1e-9, keep_grids=True)
+    ms = model_sets(mech, variant)
+    tg = sub.tgrid.cpu().numpy().T.copy()
+    if variant == "Eon":
+        Tp, idx = sub.Tprof.cpu().numpy().T.copy(), sub.idx_cut.cpu().numpy()
+    else:
+        Tp, idx = np.repeat(T[sel][:, None], 801, 1), np.full(len(sel), 800, np.int32)
+    truth, _ = CO.truth_batch(tg, Tp, R.inlet_concentration(T[sel], P[sel]), ms.crnn.w_in, ms.crnn.w_b, ms.crnn.w_out, upto=idx, nthreads=8)
+    assert np.max(rel_err(sub.y.cpu().numpy().T, np.clip(truth, 1e-6, 60.0))) < 1e-6
+
+
 def test_predict_n_ode_and_crnn_predict_seams(surrogates, golden):
     """Reference seam shapes: predict_n_ode -> [801, 9, n] on the MLP grid; crnn_predict -> [9, 801]."""
     s = surrogates("LLNL", "Eon")
