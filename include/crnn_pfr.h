@@ -63,6 +63,11 @@ int crnn_model_destroy(crnn_model_t m);
 int pfr_mlp_create(int in_dim, const float* const weights[4], const float* const biases[4], double out_min,
                    double out_max, const double* in_lo, const double* in_hi, pfr_mlp_t* out);
 int pfr_mlp_destroy(pfr_mlp_t mlp);
+/* Arithmetic of the three 512-wide layers: PFR_MLP_FP32 = FP32 FFMA, one accumulator per output, k ascending (default);
+ * PFR_MLP_TF32X3 = tcgen05 tensor cores with an error-compensated 3xTF32 split (float32 accumulation in TMEM). */
+#define PFR_MLP_FP32 0
+#define PFR_MLP_TF32X3 1
+int pfr_mlp_set_mode(pfr_mlp_t mlp, int mode);
 /* scratch needed by the calls below for batches processed `chunk` conditions at a time (chunk<=0: default) */
 size_t pfr_mlp_workspace_bytes(int n, int chunk);
 

@@ -36,6 +36,8 @@ def _declare(lib):
     lib.pfr_mlp_create.argtypes = [c_int, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), c_double, c_double,
                                    c_double_p, c_double_p, ctypes.POINTER(c_void_p)]
     lib.pfr_mlp_destroy.argtypes = [c_void_p]
+    lib.pfr_mlp_set_mode.argtypes = [c_void_p, c_int]
+    lib.pfr_mlp_set_mode.restype = c_int
     lib.pfr_mlp_workspace_bytes.restype = c_size_t
     lib.pfr_mlp_workspace_bytes.argtypes = [c_int, c_int]
     lib.pfr_inlet_concentration.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]

@@ -15,6 +15,7 @@
 #include "integrate_rodas_coop.cuh"
 #include "adjoint.cuh"
 #include "mlp.cuh"
+#include "mlp_tc.cuh"
 
 using namespace pfr;
 
@@ -48,7 +49,46 @@ struct pfr_mlp {
     float *W1, *b1, *Wt2, *b2, *Wt3, *b3, *Wt4, *b4;
     float span, omin;
     MlpInputScale sc;
+    // tensor-core path (mlp_tc.cuh): TF32 hi/lo split of fc2..fc4 in nn.Linear layout [out][512] and their TMA maps
+    int mode;  // PFR_MLP_FP32 | PFR_MLP_TF32X3
+    float *Whi[3], *Wlo[3];
+    CUtensorMap mapWhi[3], mapWlo[3];
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn g_encode = nullptr;
+static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return cuda_fail(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point");
+        g_encode = (encode_tiled_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)tc::KDIM, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)tc::KDIM * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return PFR_ECUDA;
+    }
+    return PFR_OK;
+}
+
+static inline float host_rn_tf32(float x) {  // round to nearest (ties away) on the 13 dropped mantissa bits, like cvt.rna.tf32.f32
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
 
 // log / exp tables of fastmath.cuh, computed once per process in long double and kept in device memory
 static FastTables* g_tables = nullptr;
@@ -178,13 +218,41 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
     h.assign(m->npad4, 0.f);
     for (int o = 0; o < MLP_OUT; o++) h[o] = biases[3][o];
     if ((rc = upload(h, &m->b4))) return rc;
+    // tensor-core path: fc2..fc4 as TF32 hi/lo pairs, nn.Linear layout
+    for (int l = 0; l < 3; l++) {
+        const int rows = l < 2 ? MLP_HID : MLP_OUT;
+        std::vector<float> hi((size_t)rows * MLP_HID), lo((size_t)rows * MLP_HID);
+        for (size_t e = 0; e < hi.size(); e++) {
+            hi[e] = host_rn_tf32(weights[l + 1][e]);
+            lo[e] = host_rn_tf32(weights[l + 1][e] - hi[e]);
+        }
+        if ((rc = upload(hi, &m->Whi[l]))) return rc;
+        if ((rc = upload(lo, &m->Wlo[l]))) return rc;
+    }
+    m->mode = PFR_MLP_FP32;
     *out = m;
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_set_mode(pfr_mlp_t m, int mode) {
+    if (!m || (mode != PFR_MLP_FP32 && mode != PFR_MLP_TF32X3)) return PFR_EINVAL;
+    if (mode == PFR_MLP_TF32X3) {
+        for (int l = 0; l < 3; l++) {
+            const int rows = l < 2 ? MLP_HID : MLP_OUT;
+            const uint32_t box = tc::BN;   // the 800-row output layer's last tile reads past the end: TMA zero-fills
+            int rc;
+            if ((rc = make_map_2d(&m->mapWhi[l], m->Whi[l], rows, box))) return rc;
+            if ((rc = make_map_2d(&m->mapWlo[l], m->Wlo[l], rows, box))) return rc;
+        }
+    }
+    m->mode = mode;
     return PFR_OK;
 }
 
 extern "C" int pfr_mlp_destroy(pfr_mlp_t m) {
     if (!m) return PFR_OK;
-    float* ptrs[8] = {m->W1, m->b1, m->Wt2, m->b2, m->Wt3, m->b3, m->Wt4, m->b4};
+    float* ptrs[14] = {m->W1, m->b1, m->Wt2, m->b2, m->Wt3, m->b3, m->Wt4, m->b4, m->Whi[0], m->Whi[1], m->Whi[2],
+                       m->Wlo[0], m->Wlo[1], m->Wlo[2]};
     for (float* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -193,8 +261,8 @@ extern "C" int pfr_mlp_destroy(pfr_mlp_t m) {
 
 extern "C" size_t pfr_mlp_workspace_bytes(int n, int chunk) {
     const size_t ld = (size_t)eff_chunk(n, chunk);
-    // two activation buffers [512][ld] + one output scratch [800][ld] (t_end-only mode)
-    return (2 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float);
+    // FP32 path: two activation buffers [512][ld]; tensor-core path: two hi/lo pairs [ld][512]; + one output scratch [800][ld]
+    return (4 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float);
 }
 
 extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, float* c0, void* stream) {
@@ -207,16 +275,78 @@ extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, fl
     return PFR_OK;
 }
 
+// Tensor-core variant of mlp_run's chunk loop (mlp_tc.cuh): activations [ld][512] as TF32 hi/lo pairs, three tcgen05 GEMMs.
+template <bool kFinal>
+static int launch_tc_gemm(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
+                          const tc::GemmArgs& g, int n_tiles, int m_tiles, cudaStream_t st) {
+    auto kern = tc::mlp_tc_gemm_kernel<kFinal>;
+    const size_t smem = (size_t)tc::STAGES * (2 * tc::BM * tc::BK * 4 + 2 * tc::BN * tc::BK * 4) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<dim3(n_tiles, m_tiles), tc::THREADS, smem, st>>>(ahi, alo, bhi, blo, g);
+    CK_LAUNCH("mlp_tc_gemm_kernel");
+    return PFR_OK;
+}
+
+static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
+                      float* t_end, bool is_time, int raw, float* H, float* S, int ld, cudaStream_t st) {
+    float* Ahi = H;
+    float* Alo = H + (size_t)MLP_HID * ld;
+    float* Bhi = H + (size_t)2 * MLP_HID * ld;
+    float* Blo = H + (size_t)3 * MLP_HID * ld;
+    CUtensorMap mA[2][2];
+    int rc;
+    if ((rc = make_map_2d(&mA[0][0], Ahi, ld, tc::BM)) || (rc = make_map_2d(&mA[0][1], Alo, ld, tc::BM)) ||
+        (rc = make_map_2d(&mA[1][0], Bhi, ld, tc::BM)) || (rc = make_map_2d(&mA[1][1], Blo, ld, tc::BM)))
+        return rc;
+    const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
+    for (int c0 = 0; c0 < n; c0 += ld) {
+        const int mv = (n - c0) < ld ? (n - c0) : ld;
+        const int rows = round_up(mv, tc::BM);
+        const size_t elems = (size_t)rows * MLP_HID;
+        tc::mlp_tc_layer1_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(
+            m->W1, m->b1, m->in_dim, m->sc.lo[0], m->sc.lo[1], m->sc.lo[2], m->sc.lo[3], m->sc.span[0], m->sc.span[1],
+            m->sc.span[2], m->sc.span[3], m->sc.fullL, m->sc.fullU, T + c0, P + c0, L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv,
+            rows, Ahi, Alo);
+        CK_LAUNCH("mlp_tc_layer1_kernel");
+        tc::GemmArgs g2{m->b2, Bhi, Blo, 0, 0, 0, 1.f, 0.f};
+        if ((rc = launch_tc_gemm<false>(mA[0][0], mA[0][1], m->mapWhi[0], m->mapWlo[0], g2, MLP_HID / tc::BN, rows / tc::BM, st))) return rc;
+        tc::GemmArgs g3{m->b3, Ahi, Alo, 0, 0, 0, 1.f, 0.f};
+        if ((rc = launch_tc_gemm<false>(mA[1][0], mA[1][1], m->mapWhi[1], m->mapWlo[1], g3, MLP_HID / tc::BN, rows / tc::BM, st))) return rc;
+        float* out_rows = grid ? grid + (size_t)n + c0 : S;
+        const size_t out_ld = grid ? (size_t)n : (size_t)ld;
+        tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin};
+        if ((rc = launch_tc_gemm<true>(mA[0][0], mA[0][1], m->mapWhi[2], m->mapWlo[2], g4, (MLP_OUT + tc::BN - 1) / tc::BN, rows / tc::BM, st))) return rc;
+        if (is_time) {
+            if (!raw) {
+                enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, st>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,
+                                                                        t_end ? t_end + c0 : nullptr, grid ? 1 : 0);
+                CK_LAUNCH("enforce_strict_kernel");
+            } else if (grid) {
+                CK(cudaMemsetAsync(grid + c0, 0, (size_t)mv * sizeof(float), st));
+            }
+        } else {
+            copy_row_kernel<<<(mv + 255) / 256, 256, 0, st>>>(T + c0, grid + c0, mv);
+            CK_LAUNCH("copy_row_kernel");
+        }
+    }
+    return PFR_OK;
+}
+
 // Shared driver of pfr_time_grid / pfr_temp_profile: chunks of `ld` conditions through the four layers.
 static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
                    float* t_end, bool is_time, int raw, void* ws, size_t ws_bytes, int chunk, cudaStream_t st) {
     if (n == 0) return PFR_OK;
     if (!m || !T || !P || n < 0 || (!grid && !t_end) || !ws) return PFR_EINVAL;
     const int ld = eff_chunk(n, chunk);
-    if (ws_bytes < (2 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float)) return PFR_EWORKSPACE;
+    if (ws_bytes < (4 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float)) return PFR_EWORKSPACE;
     float* H1 = static_cast<float*>(ws);
     float* H2 = H1 + (size_t)MLP_HID * ld;
-    float* S = H2 + (size_t)MLP_HID * ld;  // [800][ld] scratch for the t_end-only mode
+    float* S = H1 + (size_t)4 * MLP_HID * ld;  // [800][ld] scratch for the t_end-only mode
+    if (m->mode == PFR_MLP_TF32X3) return mlp_run_tc(m, T, P, L, U, n, grid, t_end, is_time, raw, H1, S, ld, st);
     const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
     for (int c0 = 0; c0 < n; c0 += ld) {
         const int mv = (n - c0) < ld ? (n - c0) : ld;

@@ -70,7 +70,7 @@ class CrnnModel:
 class MlpModel:
     """Device-side handle of one 512-wide predictor MLP (pfr_mlp_create); weights are uploaded once."""
 
-    def __init__(self, params: MLPParams):
+    def __init__(self, params: MLPParams, mode: str = "tf32x3"):
         self.params = params
         self.in_dim = params.in_dim
         W = (_lib.c_float_p * 4)(*[a.ctypes.data_as(_lib.c_float_p) for a in params.w])
@@ -81,6 +81,12 @@ class MlpModel:
         _lib.check(_lib.lib().pfr_mlp_create(self.in_dim, W, B, params.out_min, params.out_max, lo, hi, ctypes.byref(h)),
                    "pfr_mlp_create")
         self.handle = h
+        self.set_mode(mode)
+
+    def set_mode(self, mode: str):
+        """'fp32': FP32 FFMA layers (fixed summation order); 'tf32x3': tcgen05 tensor cores, 3xTF32 split."""
+        _lib.check(_lib.lib().pfr_mlp_set_mode(self.handle, {"fp32": 0, "tf32x3": 1}[mode]), "pfr_mlp_set_mode")
+        self.mode = mode
 
     def __del__(self):
         try:
@@ -113,7 +119,8 @@ class SolveResult:
 class Surrogate:
     """One model variant (CRNN + time MLP [+ temperature MLP]) resident on one GPU."""
 
-    def __init__(self, models: ModelSet, device: str | torch.device = "cuda", clamps=INFERENCE_CLAMPS, chunk: int = 0):
+    def __init__(self, models: ModelSet, device: str | torch.device = "cuda", clamps=INFERENCE_CLAMPS, chunk: int = 0,
+                 mlp_mode: str = "tf32x3"):
         if not torch.cuda.is_available():
             raise _lib.PfrError("no CUDA device: this package has no CPU path")
         self.device = torch.device(device)
@@ -124,8 +131,8 @@ class Surrogate:
         self.energy_on = models.energy_on
         self.chunk = int(chunk)
         self.crnn = CrnnModel(models.crnn, clamps)
-        self.time_mlp = MlpModel(models.time_mlp)
-        self.temp_mlp = MlpModel(models.temp_mlp) if models.temp_mlp is not None else None
+        self.time_mlp = MlpModel(models.time_mlp, mlp_mode)
+        self.temp_mlp = MlpModel(models.temp_mlp, mlp_mode) if models.temp_mlp is not None else None
         self._ws = None
 
     # ------------------------------------------------------------------ plumbing

@@ -64,10 +64,10 @@ def surrogates(model_sets):
 
     cache = {}
 
-    def get(mech="LLNL", variant="Eoff", crnn_key=None):
-        key = (mech, variant, crnn_key)
+    def get(mech="LLNL", variant="Eoff", crnn_key=None, mlp_mode="tf32x3"):
+        key = (mech, variant, crnn_key, mlp_mode)
         if key not in cache:
-            cache[key] = Surrogate(model_sets(mech, variant, crnn_key))
+            cache[key] = Surrogate(model_sets(mech, variant, crnn_key), mlp_mode=mlp_mode)
         return cache[key]
 
     return get
