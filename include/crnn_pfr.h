@@ -113,7 +113,8 @@ int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float*
  * y_knots[801][9][n]: raw knot states of the forward pass (pfr_integrate with y_dense and PFR_FLAG_DENSE_RAW, double);
  * ref[801][7][n] labels (mol/m3), yscale[7][n] (...:105).  loss[n]: per-condition MSE over 7 x 801 points;
  * grad[189][n]: per-condition d loss / d (w_in[11][9] | w_b[9] | w_out[9][9]) by the continuous adjoint, RK4 with
- * `substeps` steps per knot interval.  The model's clamps are those given to crnn_model_create. */
+ * |substeps| steps per knot interval; substeps > 0: one condition per warp (the product kernel), < 0: one per thread
+ * (cross-check).  The model's clamps are those given to crnn_model_create. */
 int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof, const double* y_knots,
                   const float* ref, const float* yscale, int substeps, double* loss, double* grad, void* stream);
 /* out[r] = sum_i x[r][i] with a fixed summation tree (deterministic reduction of per-condition gradients) */

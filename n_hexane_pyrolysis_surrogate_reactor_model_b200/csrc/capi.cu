@@ -515,11 +515,20 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
                              const double* y_knots, const float* ref, const float* yscale, int substeps, double* loss,
                              double* grad, void* stream) {
     if (n == 0) return PFR_OK;
-    if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || n < 0 || substeps < 1) return PFR_EINVAL;
+    if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || n < 0 || substeps == 0) return PFR_EINVAL;
     AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad};
-    const int blocks = (n + ADJ_BLOCK - 1) / ADJ_BLOCK;
-    if (Tprof) adjoint_kernel<true><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
-    else adjoint_kernel<false><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
+    if (substeps > 0) {
+        // one condition per warp
+        const int blocks = (n + ADJW_WARPS - 1) / ADJW_WARPS;
+        if (Tprof) adjoint_warp_kernel<true><<<blocks, 32 * ADJW_WARPS, 0, (cudaStream_t)stream>>>(m->pd, a);
+        else adjoint_warp_kernel<false><<<blocks, 32 * ADJW_WARPS, 0, (cudaStream_t)stream>>>(m->pd, a);
+    } else {
+        // negative sub-step count: the one-thread-per-condition kernel (cross-check)
+        a.substeps = -substeps;
+        const int blocks = (n + ADJ_BLOCK - 1) / ADJ_BLOCK;
+        if (Tprof) adjoint_kernel<true><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
+        else adjoint_kernel<false><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
+    }
     CK_LAUNCH("adjoint_kernel");
     return PFR_OK;
 }

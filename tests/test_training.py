@@ -118,6 +118,19 @@ def test_loss_and_gradient_vs_oracle_finite_differences(surrogates, model_sets, 
 
 
 @pytest.mark.gpu
+def test_warp_and_thread_adjoint_kernels_agree(surrogates, model_sets, conditions):
+    """The one-condition-per-warp adjoint kernel (product) against the one-condition-per-thread one (same arithmetic,
+    different mapping and summation order): losses and all 189 gradient entries agree to 1e-10 of the gradient scale."""
+    tr, batch, T, P = _setup(surrogates, model_sets, conditions, n=9)
+    student = model_sets("LLNL", "Eoff").crnn
+    l1, g1, _ = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
+    tr.substeps = -2
+    l2, g2, _ = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
+    assert abs(float(l1) - float(l2)) < 1e-12 * abs(float(l2))
+    assert float((g1 - g2).abs().max()) < 1e-10 * float(g2.abs().max())
+
+
+@pytest.mark.gpu
 def test_gradient_vs_reference_style_autograd(surrogates, model_sets, conditions):
     """The reference obtains its gradient by back-propagating through torchdiffeq's dopri5 operations (float32,
     rtol 1e-4, atol 1e-6: discretise-then-differentiate).  The adjoint gradient of the SAME loss at the same
