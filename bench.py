@@ -190,6 +190,18 @@ def run_ours(args):
         del sur
         torch.cuda.empty_cache()
 
+    # the other mechanisms of config 3 and the reference-behaviour integrator, device-resident timing only
+    for mech, variant, method, prec in (("JetSurf", "Eon", "rodas4", 64), ("JetSurf", "Eoff", "rodas4", 64), ("NUIG", "Eon", "rodas4", 64),
+                                        ("NUIG", "Eoff", "rodas4", 64), ("LLNL", "Eoff", "dopri5", 32), ("LLNL", "Eon", "rodas4", 32)):
+        sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, f"{mech}.npz"), variant), device=dev)
+        kw2 = dict(method=method, precision=prec, rtol=args.rtol, atol=args.atol)
+        ms, res, _ = time_steps(lambda: gather_outlets(sur.sweep(T, P, L, U, **kw2).y, n_total), 2, 1)
+        r = sur.sweep(T, P, L, U, **kw2)
+        name = f"{mech}_{variant}" + ("" if (method, prec) == ("rodas4", 64) else f"_{method}_f{prec}")
+        variants[name] = {"value": n_total * 2 / (ms * 1e-3), "ms_per_step": ms / 2, "failed_trajectories": int((r.status != 0).sum().item()),
+                          "integrator": method, "state_dtype": f"f{prec}"}
+        del sur, r, res
+        torch.cuda.empty_cache()
     variants["train_step_WIDE_Eoff"] = training_variant(dev, world, rank, time_steps)
     if rank != 0:
         if world > 1:
