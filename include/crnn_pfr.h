@@ -120,6 +120,16 @@ int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, co
 /* out[r] = sum_i x[r][i] with a fixed summation tree (deterministic reduction of per-condition gradients) */
 int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream);
 
+/* Accuracy numbers of the reference's per-case / per-species CSV, all conditions at once
+ * (...Eoff_single_model.py:384-480, ...Eon_single_model.py:381-463).
+ * dense [801][9][n] (precision 64: double, 32: float) as pfr_integrate writes it; label [801][7][n] float at the same
+ * knots (mol/m3); idx_end [n] or NULL: last knot used (Eon trim, knots 1..idx_end; NULL = 800); abs_den != 0 divides
+ * the relative errors by |ref| + 1e-5 (Eon script) instead of ref + 1e-5 (Eoff script).
+ * out [8][7][n] double: RMSE_final, NRMSE_final, RelError_final %, RMSE_time_avg, NRMSE_time_avg, RelError_time_avg %,
+ * FCD, Max_Norm. */
+int pfr_accuracy(const void* dense, int precision, const float* label, const int* idx_end, int n, int abs_den, double* out,
+                 void* stream);
+
 /* Parity hook for the table-driven double-precision log (kind 0, x positive normal) / exp (kind 1, |x| < 700)
  * used inside the Rosenbrock kernel in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).
  * x[n] -> y[n], device pointers. */

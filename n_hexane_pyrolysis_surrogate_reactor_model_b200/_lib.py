@@ -55,6 +55,8 @@ def _declare(lib):
     lib.pfr_loss_grad.restype = c_int
     lib.pfr_reduce_rows.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.pfr_reduce_rows.restype = c_int
+    lib.pfr_accuracy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.pfr_accuracy.restype = c_int
     lib.pfr_measure_peaks.argtypes = [c_double_p]
     lib.pfr_fastmath.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.pfr_fastmath.restype = c_int

@@ -406,6 +406,19 @@ extern "C" int pfr_idx_cut(const float* t_full, const float* t_end, int n, int* 
     return PFR_OK;
 }
 
+extern "C" int pfr_accuracy(const void* dense, int precision, const float* label, const int* idx_end, int n, int abs_den,
+                            double* out, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!dense || !label || !out || n < 0 || (precision != 32 && precision != 64)) return PFR_EINVAL;
+    const int total = n * 7;
+    if (precision == 64)
+        accuracy_kernel<double><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const double*)dense, label, idx_end, n, 7, abs_den, out);
+    else
+        accuracy_kernel<float><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)dense, label, idx_end, n, 7, abs_den, out);
+    CK_LAUNCH("accuracy_kernel");
+    return PFR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <typename real>
 __global__ void __launch_bounds__(128)

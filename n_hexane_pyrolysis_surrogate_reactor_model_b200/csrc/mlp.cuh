@@ -186,6 +186,48 @@ idx_cut_kernel(const float* __restrict__ t_full, size_t ld, const float* __restr
     idx[i] = bi;
 }
 
+// ---- per-case / per-species accuracy numbers of the reference's CSV (...Eoff_single_model.py:384-480) ----
+// One thread per (species, condition); knots 1..kend (the t = 0 column is excluded like `true[1:]`).  Predictions are
+// rounded to float32 first (the reference's are float32), sums are carried in float64.
+// out[m][s][i], m = rmse_final, nrmse_final, rel_final %, rmse_time, nrmse_time, rel_time %, fcd, max_norm
+template <typename real>
+__global__ void __launch_bounds__(256)
+accuracy_kernel(const real* __restrict__ dense, const float* __restrict__ label, const int* __restrict__ idx_end, int n, int nobs,
+                int abs_den, double* __restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * nobs) return;
+    const int i = g % n, s = g / n;
+    const int kend = idx_end ? idx_end[i] : MLP_OUT;
+    const double eps = 1.0e-5;
+    double sp = 0, st = 0, spp = 0, stt = 0, se2 = 0, srel = 0, tmax = -1e300, tmin = 1e300, amax = 0, emax = 0, pl = 0, tl = 0;
+    for (int k = 1; k <= kend; k++) {
+        const double p = (double)(float)dense[((size_t)k * 9 + s) * n + i];
+        const double t = (double)label[((size_t)k * nobs + s) * n + i];
+        const double e = p - t;
+        sp += p; st += t; spp += p * p; stt += t * t; se2 += e * e;
+        srel += fabs(e) / ((abs_den ? fabs(t) : t) + eps);
+        tmax = fmax(tmax, t); tmin = fmin(tmin, t); amax = fmax(amax, fabs(t)); emax = fmax(emax, fabs(e));
+        pl = p; tl = t;
+    }
+    const size_t ld = (size_t)nobs * n, o = (size_t)s * n + i;
+    if (kend < 1) {
+        for (int m = 0; m < 8; m++) out[m * ld + o] = nan("");
+        return;
+    }
+    const double cnt = (double)kend, span = tmax - tmin + eps;
+    const double mp = sp / cnt, mt = st / cnt;
+    const double sdp = sqrt(fmax(spp / cnt - mp * mp, 0.0)), sdt = sqrt(fmax(stt / cnt - mt * mt, 0.0));
+    const double rf = fabs(pl - tl), rt = sqrt(se2 / cnt);
+    out[0 * ld + o] = rf;
+    out[1 * ld + o] = rf / span;
+    out[2 * ld + o] = rf / ((abs_den ? fabs(tl) : tl) + eps) * 100.0;
+    out[3 * ld + o] = rt;
+    out[4 * ld + o] = rt / span;
+    out[5 * ld + o] = srel / cnt * 100.0;
+    out[6 * ld + o] = sqrt((mt - mp) * (mt - mp) + (sdt - sdp) * (sdt - sdp));
+    out[7 * ld + o] = emax / (amax + eps);
+}
+
 // ---- row 0 of the temperature profile = T0 ----
 __global__ void __launch_bounds__(256) copy_row_kernel(const float* __restrict__ src, float* __restrict__ dst, int m) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,7 +4,9 @@
       SURROGATE_MODEL/surrogate_model_Eon_single_model.py:338-368, ...Eoff_single_model.py:345-372
   RMSE / NRMSE / relative error (final and residence-time average), Frechet-type distance, max-norm per case and species
       ...Eoff_single_model.py:384-480, ...Eon_single_model.py:381-463
-These run on the host from the [801, 9, n] dense trajectories a Surrogate returns; they are reporting, not hot path.
+The file writers run on the host; the accuracy numbers of a whole batch come from one kernel (accuracy_device /
+accuracy_rows_device, C entry point pfr_accuracy) that reads the [801, 9, n] dense trajectories where the integrator
+left them.  accuracy_rows is the single-condition host form of the same formulas.
 """
 from __future__ import annotations
 
@@ -62,6 +64,38 @@ def accuracy_rows(case_id, pred, true, T, P, L, u0, absolute_denominator=False):
     max_norm = np.max(np.abs(pred - true), axis=1) / (np.max(np.abs(true), axis=1) + EPS_REL)
     return [[case_id, SPECIES_OBS[s], T, P, L, u0, rmse_final[s], rmse_final[s] / span[s], rel_final[s], rmse_time[s],
              rmse_time[s] / span[s], rel_time[s], fcd[s], max_norm[s]] for s in range(7)]
+
+
+METRICS = COLUMNS[6:]
+
+
+def accuracy_device(dense, labels, idx_cut=None, absolute_denominator=False):
+    """[8, 7, n] float64 CUDA tensor of the eight CSV numbers for every condition and observed species.
+    dense [801, 9, n] float64/float32 CUDA (SolveResult.dense), labels [801, 7, n] float32 CUDA at the same knots,
+    idx_cut [n] int32 CUDA for the Eon trim (knots 1..idx_cut) or None."""
+    import torch
+
+    from . import _lib
+    from .surrogate import _ptr, _stream
+    n = dense.shape[2]
+    if tuple(dense.shape[:2]) != (NTOT, 9) or tuple(labels.shape) != (NTOT, 7, n) or labels.dtype != torch.float32:
+        raise ValueError("dense must be [801, 9, n], labels [801, 7, n] float32")
+    dense, labels = dense.contiguous(), labels.contiguous()
+    idx = None if idx_cut is None else idx_cut.to(torch.int32).contiguous()
+    out = torch.empty((8, 7, n), dtype=torch.float64, device=dense.device)
+    _lib.check(_lib.lib().pfr_accuracy(_ptr(dense), 64 if dense.dtype == torch.float64 else 32, _ptr(labels), _ptr(idx), n,
+                                       int(bool(absolute_denominator)), _ptr(out), _stream()), "pfr_accuracy")
+    return out
+
+
+def accuracy_rows_device(dense, labels, T, P, L, u0, idx_cut=None, absolute_denominator=False):
+    """The reference CSV rows (case-major, species inside, Case_ID 1-based) for a whole batch from accuracy_device."""
+    m = accuracy_device(dense, labels, idx_cut, absolute_denominator).cpu().numpy()
+    rows = []
+    for i in range(m.shape[2]):
+        for s in range(7):
+            rows.append([i + 1, SPECIES_OBS[s], T[i], P[i], L[i], u0[i]] + [m[k, s, i] for k in range(8)])
+    return rows
 
 
 def nearest_time_labels(t_pred, t_label, y_label):

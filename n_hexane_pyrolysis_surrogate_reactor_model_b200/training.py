@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from .containers import CRNNParams
-from .surrogate import NS, NTOTAL, TRAINING_WIDE_CLAMPS, CrnnModel, Surrogate, _ptr, _stream
+from .surrogate import NS, NTOTAL, TRAINING_NARROW_CLAMPS, TRAINING_WIDE_CLAMPS, CrnnModel, Surrogate, _ptr, _stream
 
 NR = 9
 NPAR = 189
@@ -49,6 +49,40 @@ class ConverterSpec:
 
 WIDE_LLNL = ConverterSpec()                                                    # WIDE_Eoff...:25-29,48-52
 NARROW = dict(wout=(-2.0, 2.0), win=(0.0, 2.0), Ea=(10.0, 200.0), b=(-3.0, 3.0), A=(3.0, 21.0))   # Eon...:51-56
+NARROW_FITS = {"LLNL": (2.3263, 67.933), "NUIG": (1.858, 58.397), "JetSurf": (2.1133, 61.713)}     # (b_fit, Ea_fit)  Eon...:31-40
+
+
+def narrow_spec(form: str, mechanism: str = "LLNL") -> ConverterSpec:
+    """ConverterSpec of the narrow-range trainers: form 'eon' (Eon_surrogate_model_training.py:287-327) or 'eoff'
+    (Eoff_surrogate_model_training.py:204-244) with the mechanism's Arrhenius fits."""
+    b_fit, Ea_fit = NARROW_FITS[mechanism]
+    return ConverterSpec(form=form, b_fit=b_fit, Ea_fit=Ea_fit, **NARROW)
+
+
+@dataclass
+class TrainerSettings:
+    """Solver tolerances, RHS clamps and optimiser constants of one reference trainer script."""
+    clamps: tuple
+    rtol: float
+    atol: float
+    lr: float
+    weight_decay: float
+    clip: float
+    lr_factor: float      # ReduceLROnPlateau factor (patience 5, threshold 1e-4 rel everywhere)
+
+
+WIDE_EOFF_SETTINGS = TrainerSettings(TRAINING_WIDE_CLAMPS, 1e-4, 1e-6, 5e-4, 1e-4, 10.0, 0.8)        # WIDE_Eoff...:16-19,383,500-501
+NARROW_EOFF_SETTINGS = TrainerSettings(TRAINING_NARROW_CLAMPS, 1e-2, 1e-3, 5e-3, 1e-2, 10.0, 0.6)    # Eoff...:20,397,514-515 (AdamW default wd)
+NARROW_EON_SETTINGS = TrainerSettings(TRAINING_NARROW_CLAMPS, 1e-2, 1e-3, 5e-3, 1e-2, 10.0, 0.5)     # Eon...:22,480,597-598
+
+
+def split_indices(n_exp: int, seed: int = 42):
+    """train / valid / test condition indices exactly as the trainers draw them (WIDE_Eoff...:57-58, Eon...:61-62):
+    sklearn train_test_split 80/20 then 50/50 of the remainder, random_state 42."""
+    from sklearn.model_selection import train_test_split
+    train_idx, temp_idx = train_test_split(np.arange(n_exp), test_size=0.2, random_state=seed)
+    valid_idx, test_idx = train_test_split(temp_idx, test_size=0.5, random_state=seed)
+    return train_idx, valid_idx, test_idx
 
 
 class ParameterConverter:
@@ -109,6 +143,13 @@ class TrainingBatch:
     def yscale_from_labels(ref: torch.Tensor) -> torch.Tensor:
         return torch.clamp(ref.amax(dim=0) - ref.amin(dim=0), min=1e-6)
 
+    def subset(self, idx) -> "TrainingBatch":
+        """The conditions `idx` (any order) as a new contiguous batch -- a mini-batch or the train/valid/test part."""
+        ix = torch.as_tensor(np.asarray(idx, np.int64), device=self.T0.device)
+        pick = lambda x, d: None if x is None else x.index_select(d, ix).contiguous()
+        return TrainingBatch(pick(self.T0, 0), pick(self.c0, 0), pick(self.tgrid, 1), pick(self.Tprof, 1), pick(self.ref, 2),
+                             pick(self.yscale, 1))
+
 
 def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     """Sum [grad(189) | loss | count] over the ranks (the step's only collective); identity without a process group."""
@@ -122,7 +163,11 @@ class CrnnTrainer:
     """loss / gradient / optimiser step for the flat parameter vector p[189]."""
 
     def __init__(self, batch: TrainingBatch, spec: ConverterSpec = WIDE_LLNL, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-4, atol=1e-6,
-                 substeps=2, lr=5e-4, weight_decay=1e-4, clip=10.0, group=None):
+                 substeps=2, lr=5e-4, weight_decay=1e-4, clip=10.0, group=None, settings: "TrainerSettings | None" = None):
+        if settings is not None:
+            clamps, rtol, atol, lr, weight_decay, clip = (settings.clamps, settings.rtol, settings.atol, settings.lr,
+                                                          settings.weight_decay, settings.clip)
+        self.settings = settings
         self.batch, self.clamps, self.rtol, self.atol, self.substeps = batch, clamps, rtol, atol, substeps
         self.device = batch.T0.device
         self.converter = ParameterConverter(spec)
@@ -135,18 +180,18 @@ class CrnnTrainer:
         self._sur.energy_on = batch.Tprof is not None
 
     # ---------------------------------------------------------------- device part
-    def forward(self, w_in, w_b, w_out):
+    def forward(self, w_in, w_b, w_out, batch: TrainingBatch | None = None):
         """Raw knot states [801, 9, n] (float64) of the current parameters; status [n]."""
         crnn = CrnnModel(CRNNParams(w_in, w_b, w_out), self.clamps)
         self._sur.crnn = crnn
-        b = self.batch
+        b = batch or self.batch
         res = self._sur.integrate(b.T0, b.c0, tgrid=b.tgrid, Tprof=b.Tprof, rtol=self.rtol, atol=self.atol, dense=True, dense_raw=True)
         return crnn, res
 
-    def loss_grad_w(self, w_in, w_b, w_out):
+    def loss_grad_w(self, w_in, w_b, w_out, batch: TrainingBatch | None = None):
         """(sum of per-condition losses, sum of per-condition gradients [189], failed count) on this rank, float64 CUDA."""
-        b = self.batch
-        crnn, res = self.forward(w_in, w_b, w_out)
+        b = batch or self.batch
+        crnn, res = self.forward(w_in, w_b, w_out, b)
         n = b.n
         loss = torch.empty(n, dtype=torch.float64, device=self.device)
         grad = torch.empty((NPAR, n), dtype=torch.float64, device=self.device)
@@ -158,12 +203,14 @@ class CrnnTrainer:
         return out[NPAR], out[:NPAR], int((res.status != 0).sum())
 
     # ---------------------------------------------------------------- host part (189 numbers)
-    def loss_and_grad(self, p: torch.Tensor):
-        """Mean loss over all ranks' conditions and its gradient with respect to p (float32 CPU tensors)."""
+    def loss_and_grad(self, p: torch.Tensor, idx=None):
+        """Mean loss over all ranks' conditions (or over this rank's conditions `idx`, a mini-batch) and its gradient
+        with respect to p (float32 CPU tensors)."""
+        b = self.batch if idx is None else self.batch.subset(idx)
         pc = p.detach().to("cpu", torch.float32).requires_grad_(True)
         w_in, w_b, w_out = self.converter(pc)
-        lsum, gsum, bad = self.loss_grad_w(w_in.detach().numpy(), w_b.detach().numpy(), w_out.detach().numpy())
-        packed = torch.cat([gsum, lsum.reshape(1), torch.tensor([float(self.batch.n)], dtype=torch.float64, device=self.device)])
+        lsum, gsum, bad = self.loss_grad_w(w_in.detach().numpy(), w_b.detach().numpy(), w_out.detach().numpy(), b)
+        packed = torch.cat([gsum, lsum.reshape(1), torch.tensor([float(b.n)], dtype=torch.float64, device=self.device)])
         packed = allreduce_packed(packed, self.group).cpu()
         count = float(packed[NPAR + 1])
         g = (packed[:NPAR] / count).to(torch.float32)
@@ -171,11 +218,23 @@ class CrnnTrainer:
         (gp,) = torch.autograd.grad((w_in, w_b, w_out), pc, (g_in, g_b, g_out))
         return float(packed[NPAR]) / count, gp, bad
 
-    def step(self, p: torch.Tensor):
-        """One optimiser step on p (a CPU float32 leaf tensor): gradient, clip_grad_norm_(10), AdamW(5e-4, wd 1e-4)."""
+    def loss(self, p: torch.Tensor, idx=None) -> float:
+        """Mean loss over all ranks' conditions without a parameter gradient (the validation / test loop, :424-431)."""
+        b = self.batch if idx is None else self.batch.subset(idx)
+        with torch.no_grad():
+            w_in, w_b, w_out = self.converter(p.detach().to("cpu", torch.float32))
+        lsum, _, _ = self.loss_grad_w(w_in.numpy(), w_b.numpy(), w_out.numpy(), b)
+        packed = torch.zeros(NPAR + 2, dtype=torch.float64, device=self.device)
+        packed[NPAR], packed[NPAR + 1] = lsum, float(b.n)
+        packed = allreduce_packed(packed, self.group).cpu()
+        return float(packed[NPAR]) / float(packed[NPAR + 1])
+
+    def step(self, p: torch.Tensor, idx=None):
+        """One optimiser step on p (a CPU float32 leaf tensor): gradient over the whole batch (or the mini-batch `idx`),
+        clip_grad_norm_(10), AdamW(5e-4, wd 1e-4)."""
         if self.opt is None:
             self.opt = torch.optim.AdamW([p], lr=self.lr, weight_decay=self.weight_decay)
-        loss, gp, bad = self.loss_and_grad(p)
+        loss, gp, bad = self.loss_and_grad(p, idx)
         self.opt.zero_grad()
         p.grad = gp
         if self.clip:
@@ -197,20 +256,32 @@ def save_history(path: str, history: dict, final: tuple | None = None, p: torch.
 
 
 def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrainer | None" = None, save_path: str | None = None,
-          steps_per_epoch: int = 1, log=None) -> dict:
-    """Trainer.train (WIDE_Eoff...:398-476) with batched steps: per epoch `steps_per_epoch` optimiser steps, the validation
-    loss, ReduceLROnPlateau(mode min, factor 0.8, patience 5, threshold 1e-4 rel; :501), the history append and the
-    per-epoch np.savez.  Returns the history dict."""
+          steps_per_epoch: int = 1, log=None, batch_size: int | None = None, shuffle_seed: int | None = 0,
+          lr_factor: float | None = None) -> dict:
+    """Trainer.train (WIDE_Eoff...:398-476; Eon...:498-566).  Per epoch: the optimiser steps, the validation loss,
+    ReduceLROnPlateau(mode min, patience 5, threshold 1e-4 rel; factor 0.8 wide :501, 0.6 Eoff :515, 0.5 Eon :598), the
+    history append and the per-epoch np.savez.  Returns the history dict.
+
+    batch_size None : `steps_per_epoch` steps, each on the rank's whole training shard (the fast schedule).
+    batch_size B    : one pass over the shuffled conditions in mini-batches of B; B = 1 is the reference's own schedule
+                      (random.shuffle(train_idx), one optimiser step per sample, train loss = mean of the per-step losses).
+    With several ranks every rank must hold the same number of conditions so that the step counts agree."""
     history = {"train_loss": [], "valid_loss": [], "parameters": []}
     sched = None
+    if lr_factor is None:
+        lr_factor = trainer.settings.lr_factor if trainer.settings is not None else 0.8
+    rng = np.random.default_rng(shuffle_seed)
     for epoch in range(epochs):
-        losses = [trainer.step(p)[0] for _ in range(steps_per_epoch)]
+        if batch_size is None:
+            losses = [trainer.step(p)[0] for _ in range(steps_per_epoch)]
+        else:
+            order = np.arange(trainer.batch.n) if shuffle_seed is None else rng.permutation(trainer.batch.n)
+            losses = [trainer.step(p, order[s:s + batch_size])[0] for s in range(0, len(order), batch_size)]
         if sched is None:
-            sched = torch.optim.lr_scheduler.ReduceLROnPlateau(trainer.opt, mode="min", factor=0.8, patience=5, threshold=1e-4,
+            sched = torch.optim.lr_scheduler.ReduceLROnPlateau(trainer.opt, mode="min", factor=lr_factor, patience=5, threshold=1e-4,
                                                                threshold_mode="rel")
         history["train_loss"].append(float(np.mean(losses)))
-        with torch.no_grad():
-            vloss = (valid or trainer).loss_and_grad(p)[0]
+        vloss = (valid or trainer).loss(p)
         sched.step(vloss)
         history["valid_loss"].append(float(vloss))
         w_in, w_b, w_out = (x.detach().cpu().numpy() for x in trainer.converter(p.detach()))
@@ -227,14 +298,18 @@ def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrai
 
 def synthetic_labels(sur: Surrogate, teacher: CRNNParams, T, P, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-10, atol=1e-12) -> TrainingBatch:
     """Training batch with teacher-generated labels (the reference's Cantera label files are not shipped): time grid
-    from the surrogate's time MLP at (T, P, 1.0 m, 2.5 m/s), isothermal, labels = teacher CRNN trajectories at the knots."""
+    from the surrogate's time MLP at (T, P, 1.0 m, 2.5 m/s), labels = teacher CRNN trajectories at the knots.  With an
+    Eoff model set the batch is isothermal; with an Eon set the temperature profile comes from the temperature MLP at
+    (T, P), which is what the Eon trainer integrates along (Eon_surrogate_model_training.py:118-180)."""
     T = torch.as_tensor(np.asarray(T, np.float32)).to(sur.device)
     P = torch.as_tensor(np.asarray(P, np.float32)).to(sur.device)
     c0 = sur.inlet_concentration(T, P)
     tgrid, _ = sur.time_grid(T, P, None, None)
+    Tprof = sur.temp_profile(T, P) if sur.energy_on else None
     helper = Surrogate.__new__(Surrogate)
     helper.device = sur.device
+    helper.energy_on = sur.energy_on
     helper.crnn = CrnnModel(teacher, clamps)
-    res = helper.integrate(T, c0, tgrid=tgrid, rtol=rtol, atol=atol, dense=True).raise_on_failure()
+    res = helper.integrate(T, c0, tgrid=tgrid, Tprof=Tprof, rtol=rtol, atol=atol, dense=True).raise_on_failure()
     ref = res.dense[:, :7, :].to(torch.float32).contiguous()
-    return TrainingBatch(T, c0, tgrid, None, ref, TrainingBatch.yscale_from_labels(ref).contiguous())
+    return TrainingBatch(T, c0, tgrid, Tprof, ref, TrainingBatch.yscale_from_labels(ref).contiguous())

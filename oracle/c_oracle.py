@@ -112,6 +112,11 @@ def training_loss(yk, ref, yscale, lb=1e-6, ub=60.0):
     return np.mean(d * d, axis=(1, 2))
 
 
+def set_lb(lb: float = 1.0e-6) -> None:
+    """State clamp lower bound used by every C-oracle RHS (process-global; tests restore 1e-6)."""
+    lib().oracle_set_lb(ctypes.c_double(lb))
+
+
 def rhs_batch(T, u, w_in, w_b, w_out, inter=(-30.0, 30.0)):
     T = np.ascontiguousarray(T, np.float64)
     u = np.ascontiguousarray(u, np.float64)

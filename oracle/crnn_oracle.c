@@ -42,7 +42,9 @@ static void parallel_for(int N, int nthreads, pf_body body, void *arg) {
 }
 
 #define NTOT 801
-#define LB_ 1.0e-6
+static double g_lb = 1.0e-6;   /* state clamp lower bound: 1e-6 inference / wide trainer, 1e-5 narrow trainers (Eon...:45) */
+#define LB_ g_lb
+void oracle_set_lb(double lb) { g_lb = lb; }
 #define UB_ 6.0e1
 /* the reference holds R_kcal in float32 (a float32 tensor in the Eoff script, a python scalar rounded to the
  * tensor dtype in the Eon script), so the model constant IS the float32-rounded value, in every precision */

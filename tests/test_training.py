@@ -13,11 +13,12 @@ from conftest import GOLDEN, cond4, packed_path, rel_err
 def test_product_converter_reproduces_reference_known_answers():
     """The product's ParameterConverter (one projector product instead of nine solves) on the reference's stored
     updated_p -> final_parameters pairs, and against the oracle's literal restatement."""
-    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import NARROW, ConverterSpec, ParameterConverter
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import NARROW, ConverterSpec, ParameterConverter, narrow_spec
     from oracle import reference_path as R
     kat = np.load(f"{GOLDEN}/converter_kat.npz")
     for name, spec, ospec in (("LLNL_Eoff_wide", ConverterSpec(), R.ConverterSpec()),
-                              ("NUIG_Eon", ConverterSpec(form="eon", b_fit=1.858, Ea_fit=58.397, **NARROW), R.narrow_spec("eon", 1.858, 58.397))):
+                              ("NUIG_Eon", ConverterSpec(form="eon", b_fit=1.858, Ea_fit=58.397, **NARROW), R.narrow_spec("eon", 1.858, 58.397)),
+                              ("NUIG_Eon", narrow_spec("eon", "NUIG"), R.narrow_spec("eon", 1.858, 58.397))):
         p = torch.tensor(kat[f"{name}/updated_p"])
         w_in, w_b, w_out = ParameterConverter(spec)(p)
         assert np.max(np.abs(w_in.numpy() - kat[f"{name}/w_in"])) < 3e-6
@@ -34,6 +35,26 @@ def test_converter_gradient_has_the_reference_dead_slice():
     w_in, w_b, w_out = ParameterConverter()(p)
     (w_in.sum() + w_b.sum() + (w_out ** 2).sum()).backward()
     assert torch.all(p.grad[108:] == 0) and torch.any(p.grad[:108] != 0)
+
+
+def test_split_indices_and_batch_subsets():
+    """The 80/10/10 split the trainers draw with sklearn (random_state 42) and TrainingBatch.subset column picks."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import TrainingBatch, narrow_spec, split_indices
+    tr, va, te = split_indices(800)
+    assert (len(tr), len(va), len(te)) == (640, 80, 80)
+    assert sorted(np.concatenate([tr, va, te]).tolist()) == list(range(800))
+    tr2, _, _ = split_indices(800)
+    assert np.array_equal(tr, tr2)
+    n = 6
+    b = TrainingBatch(torch.arange(n, dtype=torch.float32), torch.arange(n, dtype=torch.float32) + 10,
+                      torch.arange(801 * n, dtype=torch.float32).view(801, n), torch.arange(801 * n, dtype=torch.float32).view(801, n) + 1,
+                      torch.arange(801 * 7 * n, dtype=torch.float32).view(801, 7, n), torch.arange(7 * n, dtype=torch.float32).view(7, n))
+    s = b.subset([4, 1])
+    assert s.n == 2 and s.T0.tolist() == [4.0, 1.0] and s.c0.tolist() == [14.0, 11.0]
+    assert torch.equal(s.tgrid, b.tgrid[:, [4, 1]]) and torch.equal(s.Tprof, b.Tprof[:, [4, 1]])
+    assert torch.equal(s.ref, b.ref[:, :, [4, 1]]) and torch.equal(s.yscale, b.yscale[:, [4, 1]]) and s.ref.is_contiguous()
+    spec = narrow_spec("eoff", "JetSurf")
+    assert (spec.form, spec.b_fit, spec.Ea_fit, spec.wout, spec.A) == ("eoff", 2.1133, 61.713, (-2.0, 2.0), (3.0, 21.0))
 
 
 def _free_port():
@@ -178,3 +199,88 @@ def test_training_steps_reduce_the_loss(surrogates, model_sets, conditions):
         assert bad == 0 and np.isfinite(loss)
         losses.append(loss)
     assert losses[-1] < losses[0]
+
+
+# ----------------------------------------------------------------------------------------------- narrow Eon trainer
+def _setup_eon(surrogates, model_sets, conditions, n=8, mech="NUIG"):
+    """Eon_surrogate_model_training.py's set-up with synthetic labels: temperature profile from the temperature MLP,
+    teacher = the stored <mech>_Eon CRNN, narrow RHS clamps (lb 1e-5, exponent +-30), converter form 'eon'."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import TRAINING_NARROW_CLAMPS
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import NARROW_EON_SETTINGS, CrnnTrainer, narrow_spec, synthetic_labels
+    a = conditions["training_2D"]
+    sel = np.linspace(0, len(a) - 1, n).astype(int)
+    T, P = a[sel, 0].astype(np.float32), (a[sel, 1] * 1e5).astype(np.float32)
+    sur = surrogates(mech, "Eon")
+    batch = synthetic_labels(sur, model_sets(mech, "Eon").crnn, T, P, clamps=TRAINING_NARROW_CLAMPS)
+    assert batch.Tprof is not None
+    return CrnnTrainer(batch, spec=narrow_spec("eon", mech), settings=NARROW_EON_SETTINGS), batch, T, P
+
+
+@pytest.mark.gpu
+def test_eon_loss_and_gradient_vs_oracle_finite_differences(surrogates, model_sets, conditions):
+    """The narrow Eon trainer's loss and gradient along MLP-predicted temperature ramps (adjoint with dT/dt terms):
+    student = JetSurf_Eon parameters against NUIG_Eon labels.  Loss to 1e-7 of the oracle's converged value, gradient to
+    2e-4 of its scale against float64 central differences of the oracle loss (state clamp lower bound 1e-5)."""
+    from oracle import c_oracle as CO
+    tr, batch, T, P = _setup_eon(surrogates, model_sets, conditions, n=6)
+    tr.rtol, tr.atol = 1e-10, 1e-12
+    student = model_sets("JetSurf", "Eon").crnn
+    lsum, gsum, bad = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
+    assert bad == 0
+    n = batch.n
+    tg = batch.tgrid.cpu().numpy().T.copy()
+    Tp = batch.Tprof.cpu().numpy().T.copy()
+    c0 = np.zeros((n, 9), np.float32)
+    c0[:, 6] = batch.c0.cpu().numpy()
+    ref = batch.ref.cpu().numpy().transpose(2, 0, 1).astype(np.float64)
+    ysc = batch.yscale.cpu().numpy().T.astype(np.float64)
+
+    def oracle_loss(w_in, w_b, w_out):
+        yk = CO.truth_knots_dp(tg, Tp, c0, w_in, w_b, w_out, inter=(-30.0, 30.0), nthreads=8)
+        return CO.training_loss(yk, ref, ysc, lb=1e-5).sum()
+
+    CO.set_lb(1e-5)
+    try:
+        w = [student.w_in.astype(np.float64), student.w_b.astype(np.float64), student.w_out.astype(np.float64)]
+        L0 = oracle_loss(*w)
+        assert abs(float(lsum) - L0) / L0 < 1e-7
+        g = gsum.cpu().numpy()
+        g_in, g_b, g_out = g[:99].reshape(11, 9), g[99:108], g[108:].reshape(9, 9)
+        scale = np.abs(g).max()
+        for which, idx in [(0, (6, 0)), (0, (9, 0)), (0, (9, 5)), (0, (10, 0)), (0, (10, 3)), (1, (0,)), (1, (7,)), (2, (6, 0)), (2, (1, 2)), (2, (4, 8))]:
+            h = 1e-6 * max(1.0, abs(w[which][idx]))
+            wp = [a.copy() for a in w]
+            wm = [a.copy() for a in w]
+            wp[which][idx] += h
+            wm[which][idx] -= h
+            fd = (oracle_loss(*wp) - oracle_loss(*wm)) / (2 * h)
+            got = (g_in, g_b, g_out)[which][idx]
+            assert abs(got - fd) < 2e-4 * scale + 1e-6 * abs(fd), (which, idx, got, fd)
+    finally:
+        CO.set_lb(1e-6)
+
+
+@pytest.mark.gpu
+def test_minibatch_schedule_and_eon_training_loop(surrogates, model_sets, conditions, tmp_path):
+    """train() on the narrow Eon trainer: (i) one un-shuffled epoch with batch_size = n is exactly one full-batch step;
+    (ii) the reference's per-sample schedule (batch_size 1, shuffled) and mini-batches of 4 both lower the validation
+    loss from the perturbed stored parameters; (iii) the history file is written in the reference's layout."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import NARROW_EON_SETTINGS, CrnnTrainer, narrow_spec, train
+    kat = np.load(f"{GOLDEN}/converter_kat.npz")
+    tr, batch, T, P = _setup_eon(surrogates, model_sets, conditions, n=8)
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.tensor(kat["NUIG_Eon/updated_p"]) + 0.03 * torch.randn(189, generator=g)
+    mk = lambda: CrnnTrainer(batch, spec=narrow_spec("eon", "NUIG"), settings=NARROW_EON_SETTINGS)
+    pa, pb = p0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+    train(mk(), pa, 1, batch_size=batch.n, shuffle_seed=None)
+    mk().step(pb)
+    assert torch.equal(pa.detach(), pb.detach())
+    for bs in (1, 4):
+        p = p0.clone().requires_grad_(True)
+        path = str(tmp_path / f"hist_{bs}.npz")
+        h = train(mk(), p, 3, batch_size=bs, save_path=path)
+        first = mk().loss(p0)
+        assert abs(first - mk().loss_and_grad(p0)[0]) < 1e-12 * first
+        assert h["valid_loss"][-1] < first, (bs, first, h["valid_loss"])
+        z = np.load(path, allow_pickle=True)
+        assert len(z["train_loss"]) == 3 and z["parameters"][-1]["w_out"].shape == (9, 9) and z["updated_p"].shape == (189,)
