@@ -114,6 +114,7 @@ def run_ours(args):
     lo, hi = shard_bounds(n_total, world, rank)
     host = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory() for a in (Th, Ph, Lh, Uh)]
     n = hi - lo
+    host_np = [h.numpy() for h in host]
     T, P, L, U = (h.to(dev) for h in host)
 
     def barrier():
@@ -129,7 +130,10 @@ def run_ours(args):
         l0 = _lib.lib().pfr_launch_count()
         e0.record()
         for _ in range(steps):
+            t_host = time.perf_counter()
             out = fn()
+            if os.environ.get("PFR_BENCH_TRACE"):
+                print(f"[trace] {getattr(fn, '__name__', 'fn')} host-side {1e3 * (time.perf_counter() - t_host):.1f} ms", file=sys.stderr, flush=True)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -150,17 +154,17 @@ def run_ours(args):
             return r
 
         def step_e2e():
-            d = [h.to(dev, non_blocking=True) for h in host]
-            r = sur.sweep(*d, **kw)
-            y = gather_outlets(r.y, n_total)
-            r.y_host = y.to("cpu", non_blocking=False)
-            r.status_host = r.status.to("cpu")
+            # the public host-buffer call: numpy conditions in, numpy outlets + status of this rank's shard out
+            # (page-locked staging inside Surrogate.sweep_host), plus the device-side gather of the whole job
+            y_host, st_host, r = sur.sweep_host(*host_np, **kw)
+            r.y_all = gather_outlets(r.y, n_total)
+            r.y_host, r.status_host = y_host, st_host
             return r
 
         steps = args.steps if headline else max(1, min(args.steps, 3))
         with ClockSampler(local) as clk:
             ms, res, launches = time_steps(step_device, steps, args.warmup if headline else 3)
-        ms_e2e, res2, _ = time_steps(step_e2e, steps, 1)
+        ms_e2e, res2, _ = time_steps(step_e2e, steps, args.warmup)
         bad = int((res.status != 0).sum().item())
         flops, work = _flops(res.stats, variant == "Eon")
         # the dominant kernel alone, on the stream it is launched on (torch's current stream)
@@ -221,7 +225,8 @@ def run_ours(args):
                    "rtol": args.rtol, "atol": args.atol, "weights": "trained reference containers (tests/golden/containers)",
                    "l2": "per-step working set (6.4 KB of grids per condition, 6.7 GB per GPU) exceeds the 126 MB L2",
                    "parallelism": f"conditions sharded over {world} rank(s); final all-gather of [9,n] outlets only"},
-        "e2e": {"value": e["e2e"], "unit": "trajectories/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (72 if args.precision == 64 else 36) * n_total + 4 * n},
+        "e2e": {"value": e["e2e"], "unit": "trajectories/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (72 if args.precision == 64 else 36) * n + 4 * n,
+                "api": "Surrogate.sweep_host (numpy in, numpy out; per rank: its shard of conditions in, its outlets + status out)"},
         "gpu_launches": int(result["launches"]),
         "clocks": result["clk"],
         "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_coop_kernel<double,ramp,knots>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,

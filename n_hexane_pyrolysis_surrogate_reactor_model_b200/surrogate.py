@@ -135,6 +135,7 @@ class Surrogate:
         self.time_mlp = MlpModel(models.time_mlp, mlp_mode)
         self.temp_mlp = MlpModel(models.temp_mlp, mlp_mode) if models.temp_mlp is not None else None
         self._ws = None
+        self._grids = {}
 
     # ------------------------------------------------------------------ plumbing
     def _workspace(self, n: int):
@@ -158,26 +159,34 @@ class Surrogate:
         return out
 
     # ------------------------------------------------------------------ a2-a5
-    def time_grid(self, T, P, L=None, u0=None, want_grid=True, want_end=False, raw=False):
+    def _scratch(self, name: str, n: int) -> torch.Tensor:
+        """A [801, n] float32 grid buffer owned by this object and reused by every sweep of the same size, so that a
+        steady stream of sweeps never goes back to the allocator for its 3.4 GB (at 2^20 conditions) grids."""
+        buf = self._grids.get(name)
+        if buf is None or buf.shape[1] != n:
+            self._grids[name] = buf = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
+        return buf
+
+    def time_grid(self, T, P, L=None, u0=None, want_grid=True, want_end=False, raw=False, out=None):
         """(tgrid[801,n] | None, t_end[n] | None).  L/u0 None -> the full-length grid at (1.0 m, 2.5 m/s)."""
         T, P = _f32(T, self.device), _f32(P, self.device)
         L = None if L is None else _f32(L, self.device)
         u0 = None if u0 is None else _f32(u0, self.device)
         n = T.numel()
         ws = self._workspace(n)
-        grid = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device) if want_grid else None
+        grid = (out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)) if want_grid else None
         tend = torch.empty(n, dtype=torch.float32, device=self.device) if want_end else None
         _lib.check(_lib.lib().pfr_time_grid(self.time_mlp.handle, _ptr(T), _ptr(P), _ptr(L), _ptr(u0), n, _ptr(grid), _ptr(tend),
                                             int(raw), _ptr(ws), ws.numel(), self.chunk, _stream()), "pfr_time_grid")
         return grid, tend
 
-    def temp_profile(self, T, P, raw=False) -> torch.Tensor:
+    def temp_profile(self, T, P, raw=False, out=None) -> torch.Tensor:
         if self.temp_mlp is None:
             raise _lib.PfrError("this model set has no temperature MLP (Eoff variant)")
         T, P = _f32(T, self.device), _f32(P, self.device)
         n = T.numel()
         ws = self._workspace(n)
-        prof = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
+        prof = out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib().pfr_temp_profile(self.temp_mlp.handle, _ptr(T), _ptr(P), n, _ptr(prof), int(raw), _ptr(ws),
                                                ws.numel(), self.chunk, _stream()), "pfr_temp_profile")
         return prof
@@ -235,8 +244,9 @@ class Surrogate:
             res = self.integrate(T, c0, t_end=tend, perm=perm, method=method, precision=precision, rtol=rtol, atol=atol)
             res.tgrid = tgrid
             return res
-        t_full, _ = self.time_grid(T, P, None, None, want_grid=True)
-        Tprof = self.temp_profile(T, P)
+        n = T.numel()
+        t_full, _ = self.time_grid(T, P, None, None, want_grid=True, out=None if keep_grids else self._scratch("t_full", n))
+        Tprof = self.temp_profile(T, P, out=None if keep_grids else self._scratch("Tprof", n))
         if L is None:
             idx = torch.full((T.numel(),), NTOTAL - 1, dtype=torch.int32, device=self.device)
             tend = t_full[NTOTAL - 1].clone()
@@ -250,6 +260,33 @@ class Surrogate:
         if not keep_grids:
             res.tgrid = res.Tprof = None
         return res
+
+    def sweep_host(self, T, P, L=None, u0=None, **kw):
+        """The sweep for HOST arrays, as the reference scripts hold their conditions: numpy float32 in, numpy out.
+        Inputs are staged through page-locked buffers owned by this object (one async copy each), the outlets [9, n] and
+        status [n] come back into page-locked buffers that are reused by the next call of the same size -- copy them if
+        they must outlive it.  Returns (y, status, result) with `result` the device-side SolveResult."""
+        cols = [None if a is None else np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in (T, P, L, u0)]
+        n = cols[0].size
+        dt = torch.float64 if kw.get("precision", 64) == 64 else torch.float32
+        key = (n, dt)
+        if getattr(self, "_pin_key", None) != key:
+            self._pin_in = torch.empty((4, n), dtype=torch.float32).pin_memory()
+            self._pin_y = torch.empty((NS, n), dtype=dt).pin_memory()
+            self._pin_st = torch.empty(n, dtype=torch.int32).pin_memory()
+            self._pin_key = key
+        dev = []
+        for j, a in enumerate(cols):
+            if a is None:
+                dev.append(None)
+                continue
+            self._pin_in[j].copy_(torch.from_numpy(a))
+            dev.append(self._pin_in[j].to(self.device, non_blocking=True))
+        res = self.sweep(*dev, **kw)
+        self._pin_y.copy_(res.y, non_blocking=True)
+        self._pin_st.copy_(res.status, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin_y.numpy(), self._pin_st.numpy(), res
 
     # ------------------------------------------------------------------ reference seams (dense trajectories)
     def predict_n_ode(self, T, P, L=None, u0=None, method="rodas4", precision=64, rtol=1e-6, atol=1e-6) -> SolveResult:

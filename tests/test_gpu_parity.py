@@ -371,6 +371,19 @@ def test_sweep_end_to_end_vs_oracle(surrogates, model_sets, conditions, mech, va
     assert np.median(rel_err(y, np.clip(truth, 1e-6, 60.0)).max(axis=1)) < 5e-6
 
 
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_sweep_host_buffers_equal_device_sweep(surrogates, conditions, variant):
+    """Surrogate.sweep_host (numpy in / numpy out through page-locked staging) returns exactly what the device-tensor
+    sweep returns, also when the staging buffers are reused and when the batch size changes."""
+    sur = surrogates("LLNL", variant)
+    for n in (100, 100, 37):
+        T, P, L, U = cond4(conditions, n=n)
+        y, st, res = sur.sweep_host(T, P, L, U)
+        ref = sur.sweep(T, P, L, U)
+        assert y.shape == (9, n) and st.shape == (n,) and not st.any()
+        assert np.array_equal(y, ref.y.cpu().numpy()) and np.array_equal(st, ref.status.cpu().numpy())
+
+
 def test_sweep_sorted_equals_unsorted(surrogates, conditions):
     T, P, L, U = cond4(conditions)
     s = surrogates("LLNL", "Eon")
