@@ -276,17 +276,29 @@ extern "C" int pfr_inlet_concentration(const float* T, const float* P, int n, fl
 }
 
 // Tensor-core variant of mlp_run's chunk loop (mlp_tc.cuh): activations [ld][512] as TF32 hi/lo pairs, three tcgen05 GEMMs.
+// development hook (library built with -DPFR_TC_TRACE): device buffers [tiles][8] receiving the per-tile time stamps of the
+// three GEMMs of the next MLP chunk; not declared in include/crnn_pfr.h
+static unsigned long long* g_tc_trace[3] = {nullptr, nullptr, nullptr};
+extern "C" int pfr_dev_set_tc_trace(unsigned long long* l2, unsigned long long* l3, unsigned long long* l4) {
+    g_tc_trace[0] = l2;
+    g_tc_trace[1] = l3;
+    g_tc_trace[2] = l4;
+    return PFR_OK;
+}
 template <bool kFinal>
 static int launch_tc_gemm(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
-                          const tc::GemmArgs& g, int n_tiles, int m_tiles, cudaStream_t st) {
+                          const tc::GemmArgs& g, cudaStream_t st) {
     auto kern = tc::mlp_tc_gemm_kernel<kFinal>;
-    const size_t smem = (size_t)tc::STAGES * (2 * tc::BM * tc::BK * 4 + 2 * tc::BN * tc::BK * 4) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaFuncSetAttribute(tc::mlp_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_DYN));
+        CK(cudaFuncSetAttribute(tc::mlp_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_DYN));
     }
-    kern<<<dim3(n_tiles, m_tiles), tc::THREADS, smem, st>>>(ahi, alo, bhi, blo, g);
+    const int total = g.n_tiles * g.m_tiles;
+    kern<<<total < num_sms ? total : num_sms, tc::THREADS, tc::SMEM_DYN, st>>>(ahi, alo, bhi, blo, g);   // persistent: one CTA per SM
     CK_LAUNCH("mlp_tc_gemm_kernel");
     return PFR_OK;
 }
@@ -306,20 +318,20 @@ static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* 
     for (int c0 = 0; c0 < n; c0 += ld) {
         const int mv = (n - c0) < ld ? (n - c0) : ld;
         const int rows = round_up(mv, tc::BM);
-        const size_t elems = (size_t)rows * MLP_HID;
-        tc::mlp_tc_layer1_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(
+        tc::mlp_tc_layer1_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, st>>>(   // 8 warps per block, 8 rows per warp
             m->W1, m->b1, m->in_dim, m->sc.lo[0], m->sc.lo[1], m->sc.lo[2], m->sc.lo[3], m->sc.span[0], m->sc.span[1],
             m->sc.span[2], m->sc.span[3], m->sc.fullL, m->sc.fullU, T + c0, P + c0, L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv,
             rows, Ahi, Alo);
         CK_LAUNCH("mlp_tc_layer1_kernel");
-        tc::GemmArgs g2{m->b2, Bhi, Blo, 0, 0, 0, 1.f, 0.f};
-        if ((rc = launch_tc_gemm<false>(mA[0][0], mA[0][1], m->mapWhi[0], m->mapWlo[0], g2, MLP_HID / tc::BN, rows / tc::BM, st))) return rc;
-        tc::GemmArgs g3{m->b3, Ahi, Alo, 0, 0, 0, 1.f, 0.f};
-        if ((rc = launch_tc_gemm<false>(mA[1][0], mA[1][1], m->mapWhi[1], m->mapWlo[1], g3, MLP_HID / tc::BN, rows / tc::BM, st))) return rc;
+        const int mt = rows / tc::BM;
+        tc::GemmArgs g2{m->b2, Bhi, Blo, 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[0]};
+        if ((rc = launch_tc_gemm<false>(mA[0][0], mA[0][1], m->mapWhi[0], m->mapWlo[0], g2, st))) return rc;
+        tc::GemmArgs g3{m->b3, Ahi, Alo, 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[1]};
+        if ((rc = launch_tc_gemm<false>(mA[1][0], mA[1][1], m->mapWhi[1], m->mapWlo[1], g3, st))) return rc;
         float* out_rows = grid ? grid + (size_t)n + c0 : S;
         const size_t out_ld = grid ? (size_t)n : (size_t)ld;
-        tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin};
-        if ((rc = launch_tc_gemm<true>(mA[0][0], mA[0][1], m->mapWhi[2], m->mapWlo[2], g4, (MLP_OUT + tc::BN - 1) / tc::BN, rows / tc::BM, st))) return rc;
+        tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin, (MLP_OUT + tc::BN - 1) / tc::BN, mt, g_tc_trace[2]};
+        if ((rc = launch_tc_gemm<true>(mA[0][0], mA[0][1], m->mapWhi[2], m->mapWlo[2], g4, st))) return rc;
         if (is_time) {
             if (!raw) {
                 enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, st>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,

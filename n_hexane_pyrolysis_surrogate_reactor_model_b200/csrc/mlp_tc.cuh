@@ -21,8 +21,9 @@
 // layers) or the float32 un-scaling (output layer, written straight into the [801][n] grid rows, coalesced over
 // conditions).
 //
-// Warp roles (192 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
-// warps 2-5 epilogue.  Two 96 KB stages; every mbarrier wait is bounded and traps instead of hanging the device.
+// Warp roles (192 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one
+// elected lane), warps 2-5 epilogue.  Three 64 KB stages + 16 KB of epilogue slabs; every mbarrier wait is bounded and
+// traps instead of hanging the device.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -107,25 +108,65 @@ struct GemmArgs {
     int n_valid;           // final: outputs to store (800)
     int m_valid;           // final: conditions to store
     float span, omin;      // final: v = out * span + omin
+    int n_tiles, m_tiles;  // tiles along the outputs / the conditions; tile t -> (t / n_tiles, t % n_tiles)
+    unsigned long long* trace;  // development (-DPFR_TC_TRACE, tools/trace_tc.py): [tiles][8] %globaltimer stamps, else nullptr
 };
 
-// one CTA: D[128 x BN] = sum over 16 k-blocks of (Ahi Bhi^T + Ahi Blo^T + Alo Bhi^T)
+constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int EPI_COLS = 16;                               // accumulator columns per epilogue slab
+constexpr uint32_t SLAB_BYTES = 32 * EPI_COLS * 4;         // one warp's [32 conditions][16 outputs] slab of one array
+constexpr uint32_t STAGING_BYTES = 4 * 2 * SLAB_BYTES;     // four epilogue warps x (hi, lo)
+constexpr size_t SMEM_DYN = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
+
+#ifdef PFR_TC_TRACE
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
+#define TC_STAMP(ptr, slot) do { if (ptr) (ptr)[slot] = gtime_ns(); } while (0)
+#else
+#define TC_STAMP(ptr, slot) do { } while (0)
+#endif
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the four accumulators' columns [16 c, 16 c + 16) of this warp's 32 TMEM lanes -> v[acc][j]  (asynchronous until wait::ld)
+__device__ __forceinline__ void tmem_load_slab(uint32_t (&v)[4][16], uint32_t tmem_d, int q, int c) {
+#pragma unroll
+    for (int acc = 0; acc < 4; acc++) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * EPI_COLS);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[acc][0]), "=r"(v[acc][1]), "=r"(v[acc][2]), "=r"(v[acc][3]), "=r"(v[acc][4]), "=r"(v[acc][5]), "=r"(v[acc][6]),
+              "=r"(v[acc][7]), "=r"(v[acc][8]), "=r"(v[acc][9]), "=r"(v[acc][10]), "=r"(v[acc][11]), "=r"(v[acc][12]),
+              "=r"(v[acc][13]), "=r"(v[acc][14]), "=r"(v[acc][15])
+            : "r"(taddr));
+    }
+}
+
+// Persistent CTA (one per SM): D[128 x BN] = sum over 16 k-blocks of (Ahi Bhi^T + Ahi Blo^T + Alo Bhi^T) for tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer runs ahead across tile boundaries (the next tile's first
+// stages load while this tile's epilogue drains TMEM); the MMA warp starts the next tile as soon as the epilogue has
+// read the last accumulator slab.  Hidden layers leave through a warp-private shared-memory transpose so that one store
+// instruction writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces; the output layer stores
+// straight into the knot-major grid, where a warp's 32 conditions are contiguous.
 template <bool kFinal>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, const GemmArgs g) {
-    constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    unsigned char* staging = smem + (size_t)STAGES * STAGE_BYTES;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float bias_s[BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int total = g.n_tiles * g.m_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
+        mbar_init(&tmem_empty_bar, 4);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -140,93 +181,139 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < NKB; kb++) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-                unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(st, &mapAhi, &full_bar[s], kb * BK, m0);
-                tma_load_2d(st + A_BYTES, &mapAlo, &full_bar[s], kb * BK, m0);
-                tma_load_2d(st + 2 * A_BYTES, &mapBhi, &full_bar[s], kb * BK, n0);
-                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBlo, &full_bar[s], kb * BK, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int n0 = (tile % g.n_tiles) * BN, m0 = (tile / g.n_tiles) * BM;
+                for (int kb = 0; kb < NKB; kb++, it++) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(st, &mapAhi, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(st + A_BYTES, &mapAlo, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(st + 2 * A_BYTES, &mapBhi, &full_bar[s], kb * BK, n0);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBlo, &full_bar[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
-            for (int kb = 0; kb < NKB; kb++) {
-                const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                    const uint32_t off = ks * UMMA_K * 4;
-                    const int kg = kb * (BK / UMMA_K) + ks;          // 0..63
-                    const int part = kg < 22 ? 0 : (kg < 43 ? 1 : 2);  // three thirds of K for the leading term
-                    const bool first = kg == 0 || kg == 22 || kg == 43;
-                    // cross terms -> accumulator 0 ; leading term -> accumulator 1 + part
-                    umma_tf32(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, kg != 0);
-                    umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1);
-                    umma_tf32(tmem_d + (uint32_t)((1 + part) * BN), umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, !first);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, lt++) {
+                unsigned long long* tr = g.trace ? g.trace + 8 * (size_t)tile : nullptr;
+                (void)tr;
+                TC_STAMP(tr, 0);
+                if (lt > 0) {   // the epilogue has read every accumulator of the previous tile
+                    mbar_wait(&tmem_empty_bar, (lt - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                umma_commit(&empty_bar[s]);  // the stage is free once these MMAs have read it
+                TC_STAMP(tr, 1);
+                for (int kb = 0; kb < NKB; kb++, it++) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                        const uint32_t off = ks * UMMA_K * 4;
+                        const int kg = kb * (BK / UMMA_K) + ks;          // 0..63
+                        const int part = kg < 22 ? 0 : (kg < 43 ? 1 : 2);  // three thirds of K for the leading term
+                        const bool first = kg == 0 || kg == 22 || kg == 43;
+                        // cross terms -> accumulator 0 ; leading term -> accumulator 1 + part
+                        umma_tf32(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, kg != 0);
+                        umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1);
+                        umma_tf32(tmem_d + (uint32_t)((1 + part) * BN), umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, !first);
+                    }
+                    umma_commit(&empty_bar[s]);  // the stage is free once these MMAs have read it
+                }
+                umma_commit(&tmem_full_bar);
+                TC_STAMP(tr, 2);
             }
-            umma_commit(&tmem_full_bar);
         }
     } else {
         // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread = one condition row
         const int q = warp & 3;
-        const int m = m0 + 32 * q + lane;
-        mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; c++) {
-            uint32_t v[4][16];
+        const int e = threadIdx.x - 64;            // 0..127
+        unsigned char* mine = staging + (size_t)q * 2 * SLAB_BYTES;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, lt++) {
+            const int n0 = (tile % g.n_tiles) * BN, m0 = (tile / g.n_tiles) * BM;
+            const int m = m0 + 32 * q + lane;
+            const float bias_mine = (kFinal && n0 + e >= g.n_valid) ? 0.f : __ldg(&g.bias[n0 + e]);
+            epi_bar_sync();                        // everybody is done with the previous tile's bias
+            bias_s[e] = bias_mine;
+            epi_bar_sync();
+            unsigned long long* tr = (g.trace && e == 0) ? g.trace + 8 * (size_t)tile : nullptr;
+            (void)tr;
+            TC_STAMP(tr, 3);
+            mbar_wait(&tmem_full_bar, lt & 1);
+            TC_STAMP(tr, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // slabs of 16 accumulator columns, software-pipelined: slab c + 1 is in flight while slab c is processed
+            uint32_t v[2][4][16];
+            tmem_load_slab(v[0], tmem_d, q, 0);
 #pragma unroll
-            for (int acc = 0; acc < 4; acc++) {
-                const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(v[acc][0]), "=r"(v[acc][1]), "=r"(v[acc][2]), "=r"(v[acc][3]), "=r"(v[acc][4]), "=r"(v[acc][5]),
-                      "=r"(v[acc][6]), "=r"(v[acc][7]), "=r"(v[acc][8]), "=r"(v[acc][9]), "=r"(v[acc][10]), "=r"(v[acc][11]),
-                      "=r"(v[acc][12]), "=r"(v[acc][13]), "=r"(v[acc][14]), "=r"(v[acc][15])
-                    : "r"(taddr));
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int o0 = n0 + c * 16;
-            float x[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                // float32 round-to-nearest sum of the three K-thirds, then the cross terms, then the bias
-                const float main = (__uint_as_float(v[1][j]) + __uint_as_float(v[2][j])) + __uint_as_float(v[3][j]);
-                const int o = o0 + j;
-                x[j] = (main + __uint_as_float(v[0][j])) + ((kFinal && o >= g.n_valid) ? 0.f : __ldg(&g.bias[o]));
-            }
-            if (!kFinal) {
-                float hi[16], lo[16];
+            for (int c = 0; c < BN / EPI_COLS; c++) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 1 < BN / EPI_COLS) {
+                    tmem_load_slab(v[(c + 1) & 1], tmem_d, q, c + 1);
+                } else {                           // last slab is in registers: hand TMEM back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar);
+                    TC_STAMP(tr, 5);
+                }
+                const uint32_t (&w)[4][16] = v[c & 1];
+                const int o0 = n0 + c * EPI_COLS;
+                float x[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    const float r = fmaxf(x[j], 0.f);
-                    hi[j] = rn_tf32(r);
-                    lo[j] = rn_tf32(r - hi[j]);
+                    // float32 round-to-nearest sum of the three K-thirds, then the cross terms, then the bias
+                    const float main = (__uint_as_float(w[1][j]) + __uint_as_float(w[2][j])) + __uint_as_float(w[3][j]);
+                    x[j] = (main + __uint_as_float(w[0][j])) + bias_s[c * EPI_COLS + j];
                 }
-                float4* ph = reinterpret_cast<float4*>(g.out_hi + (size_t)m * KDIM + o0);
-                float4* pl = reinterpret_cast<float4*>(g.out_lo + (size_t)m * KDIM + o0);
+                if (!kFinal) {
+                    float hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    ph[j] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    pl[j] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                }
-            } else if (m < g.m_valid) {  // m is chunk-local, and so is the grid pointer
+                    for (int j = 0; j < 16; j++) {
+                        const float r = fmaxf(x[j], 0.f);
+                        hi[j] = rn_tf32(r);
+                        lo[j] = rn_tf32(r - hi[j]);
+                    }
+                    // transpose through this warp's slab: lane = row on the way in (16-byte chunks XOR-swizzled by the
+                    // row so that neither side has bank conflicts), 4 lanes per row on the way out
+                    __syncwarp();                  // the previous slab has been read out
+                    const int fw = (lane >> 1) & 3;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int o = o0 + j;
-                    if (o < g.n_valid) g.out_hi[(size_t)o * g.out_ld + m] = __fadd_rn(__fmul_rn(x[j], g.span), g.omin);
+                    for (int j = 0; j < 4; j++) {
+                        *reinterpret_cast<float4*>(mine + lane * 64 + ((j ^ fw) << 4)) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        *reinterpret_cast<float4*>(mine + SLAB_BYTES + lane * 64 + ((j ^ fw) << 4)) =
+                            make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int row = (lane >> 2) + 8 * i, chunk = lane & 3, phys = chunk ^ ((row >> 1) & 3);
+                        const float4 h4 = *reinterpret_cast<const float4*>(mine + row * 64 + (phys << 4));
+                        const float4 l4 = *reinterpret_cast<const float4*>(mine + SLAB_BYTES + row * 64 + (phys << 4));
+                        const size_t off = (size_t)(m0 + 32 * q + row) * KDIM + o0 + 4 * chunk;
+                        *reinterpret_cast<float4*>(g.out_hi + off) = h4;
+                        *reinterpret_cast<float4*>(g.out_lo + off) = l4;
+                    }
+                } else if (m < g.m_valid) {  // m is chunk-local, and so is the grid pointer
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int o = o0 + j;
+                        if (o < g.n_valid) g.out_hi[(size_t)o * g.out_ld + m] = __fadd_rn(__fmul_rn(x[j], g.span), g.omin);
+                    }
                 }
             }
+            TC_STAMP(tr, 6);
+#ifdef PFR_TC_TRACE
+            if (tr) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tr[7] = sm; }
+#endif
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -237,27 +324,45 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     }
 }
 
-// layer 1 (K <= 4) fused with the input scaling, written K-major as a TF32 hi/lo pair
+// layer 1 (K <= 4) fused with the input scaling, written K-major as a TF32 hi/lo pair.
+// One warp per condition row: the four scaled inputs (IEEE divisions, as the reference computes them) once per lane,
+// then lane l produces outputs 4l..4l+3 (+128, +256, +384) so that every store instruction of the warp writes 512
+// contiguous bytes.  Memory-bound on the 4 KB it writes per condition.
 __global__ void __launch_bounds__(256)
 mlp_tc_layer1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, float lo0, float lo1, float lo2,
                      float lo3, float sp0, float sp1, float sp2, float sp3, float fullL, float fullU,
                      const float* __restrict__ T, const float* __restrict__ P, const float* __restrict__ L,
                      const float* __restrict__ U, int m_valid, int rows, float* __restrict__ Hhi, float* __restrict__ Hlo) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)rows * KDIM) return;
-    const int m = (int)(idx / KDIM), k = (int)(idx % KDIM);
-    const int ms = m < m_valid ? m : m_valid - 1;
-    float x[4];
-    x[0] = __fdiv_rn(__fsub_rn(T[ms], lo0), sp0);
-    x[1] = __fdiv_rn(__fsub_rn(P[ms], lo1), sp1);
-    x[2] = __fdiv_rn(__fsub_rn(L ? L[ms] : fullL, lo2), sp2);
-    x[3] = __fdiv_rn(__fsub_rn(U ? U[ms] : fullU, lo3), sp3);
-    float acc = 0.f;
-    for (int i = 0; i < in_dim; i++) acc = fmaf(x[i], W1[k * in_dim + i], acc);
-    acc = fmaxf(acc + b1[k], 0.f);
-    const float hi = rn_tf32(acc);
-    Hhi[idx] = hi;
-    Hlo[idx] = rn_tf32(acc - hi);
+    __shared__ float w_s[4 * KDIM], b_s[KDIM];     // w_s[i][k]: input-major copy of fc1.weight ([512][in_dim])
+    for (int e = threadIdx.x; e < KDIM; e += blockDim.x) {
+        b_s[e] = b1[e];
+        for (int i = 0; i < 4; i++) w_s[i * KDIM + e] = i < in_dim ? W1[e * in_dim + i] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < rows; m += gridDim.x * wpb) {
+        const int ms = m < m_valid ? m : m_valid - 1;
+        float x[4];
+        x[0] = __fdiv_rn(__fsub_rn(T[ms], lo0), sp0);
+        x[1] = __fdiv_rn(__fsub_rn(P[ms], lo1), sp1);
+        x[2] = in_dim > 2 ? __fdiv_rn(__fsub_rn(L ? L[ms] : fullL, lo2), sp2) : 0.f;
+        x[3] = in_dim > 2 ? __fdiv_rn(__fsub_rn(U ? U[ms] : fullU, lo3), sp3) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k0 = 128 * j + 4 * lane;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                float acc = 0.f;
+                for (int i = 0; i < in_dim; i++) acc = fmaf(x[i], w_s[i * KDIM + k0 + t], acc);   // i ascending, like the FP32 path
+                acc = fmaxf(acc + b_s[k0 + t], 0.f);
+                hi[t] = rn_tf32(acc);
+                lo[t] = rn_tf32(acc - hi[t]);
+            }
+            *reinterpret_cast<float4*>(Hhi + (size_t)m * KDIM + k0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(Hlo + (size_t)m * KDIM + k0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
 }
 
 }  // namespace tc
