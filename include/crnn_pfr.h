@@ -38,6 +38,9 @@ extern "C" {
 #define PFR_METHOD_RODAS4 0     /* adaptive Rosenbrock, knot-aware (the product integrator): 3 lanes per condition */
 #define PFR_METHOD_DOPRI5 1     /* torchdiffeq-semantics dopri5 (reference-behaviour mode) */
 #define PFR_METHOD_RODAS4_TPC 2 /* the same Rosenbrock method, one thread per condition (LU parked in shared memory) */
+#define PFR_METHOD_ROS3 3       /* 3-stage L-stable Rosenbrock of order 3(2), 2 right-hand sides per step, same kernel structure
+                                 * as PFR_METHOD_RODAS4: cheaper per knot-limited step, needs a ~10x tighter tolerance for the
+                                 * same accuracy (work-precision table) */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;

@@ -12,6 +12,7 @@ PFR_OK = 0
 METHOD_RODAS4 = 0
 METHOD_DOPRI5 = 1
 METHOD_RODAS4_TPC = 2
+METHOD_ROS3 = 3
 STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow"}
 
 c_void_p, c_int, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t

@@ -482,20 +482,20 @@ static int dispatch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStr
     return launch_rodas<real, false, false>(p, a, st);
 }
 
-template <typename real, bool kRamp, bool kKnots>
+template <typename real, bool kRamp, bool kKnots, int kMethod>
 static int launch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
     const int blocks = (a.n + COOP_PER_BLOCK - 1) / COOP_PER_BLOCK;
     const size_t dyn = PFR_AINV_SMEM ? (size_t)3 * NS * COOP_BLOCK * sizeof(real) : 0;
-    rodas4_coop_kernel<real, kRamp, kKnots><<<blocks, COOP_BLOCK, dyn, st>>>(p, a);
+    rodas4_coop_kernel<real, kRamp, kKnots, kMethod><<<blocks, COOP_BLOCK, dyn, st>>>(p, a);
     CK_LAUNCH("rodas4_coop_kernel");
     return PFR_OK;
 }
 
-template <typename real>
+template <typename real, int kMethod>
 static int dispatch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
-    if (a.Tprof) return launch_rodas_coop<real, true, true>(p, a, st);
-    if (a.y_dense || a.idx_end) return launch_rodas_coop<real, false, true>(p, a, st);
-    return launch_rodas_coop<real, false, false>(p, a, st);
+    if (a.Tprof) return launch_rodas_coop<real, true, true, kMethod>(p, a, st);
+    if (a.y_dense || a.idx_end) return launch_rodas_coop<real, false, true, kMethod>(p, a, st);
+    return launch_rodas_coop<real, false, false, kMethod>(p, a, st);
 }
 
 template <typename real>
@@ -513,7 +513,7 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
-    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3) return PFR_EINVAL;
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
@@ -525,7 +525,11 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     cudaStream_t st = (cudaStream_t)stream;
     if (method == PFR_METHOD_RODAS4) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_rodas_coop<double>(m->pd, a, st) : dispatch_rodas_coop<float>(m->pf, a, st);
+        return precision == 64 ? dispatch_rodas_coop<double, COOP_RODAS4>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_RODAS4>(m->pf, a, st);
+    }
+    if (method == PFR_METHOD_ROS3) {
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
+        return precision == 64 ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
     }
     if (method == PFR_METHOD_RODAS4_TPC) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};

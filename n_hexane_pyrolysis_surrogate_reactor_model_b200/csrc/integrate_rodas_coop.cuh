@@ -248,10 +248,35 @@ __device__ __forceinline__ void coop_solve(const real (&A)[3][NS], const real* A
     }
 }
 
-template <typename real, bool kRamp, bool kKnots>
+// ROS3 (Sandu, Verwer, Blom, Spee, Carmichael, Potra 1997): 3 stages, 2 right-hand sides, order 3(2), L-stable; the third
+// stage re-uses the second stage's right-hand side.  Written in the same transformed form as RODAS4 above
+// (E k_i = f(y + sum a_ij k_j) + sum (C_ij / h) k_j + h d_i f_t, E = I/(h gamma) - J).  Coefficients verified by an
+// order-of-convergence experiment on the CRNN itself (tools/proto/ros_proto.py: global 3.0, embedded 2.0).
+namespace ros3 {
+constexpr double gamma = 0.43586652150845899941601945119356;
+constexpr double C21 = -1.0156171083877702091975600115545;
+constexpr double C31 = 4.0759956452537699824805835358067, C32 = 9.2076794298330791242156818474003;
+constexpr double m2 = 6.1697947043828245592553615689730, m3 = -0.4277225654321857332623837380651;  // m1 = a21 = a31 = 1
+constexpr double e1 = 0.5, e2 = -2.9079558716805469821718236208017, e3 = 0.2235406989781156962736090927619;
+constexpr double c2 = gamma;
+constexpr double d1 = gamma, d2 = 0.24291996454816804366592249683314, d3 = 2.1851380027664058511513169485832;
+}  // namespace ros3
+
+constexpr int COOP_RODAS4 = 0, COOP_ROS3 = 1;
+
+// 0.9 err^(-1/(q+1)) with q the order of the embedded solution (3 for RODAS4, 2 for ROS3; the cube root in float: it only
+// scales the next step, and the three lanes of a group evaluate it on bit-identical inputs)
+template <int kMethod> __device__ __forceinline__ double ctrl_factor(double err) {
+    if (kMethod == COOP_ROS3) return (double)(0.9f / cbrtf(fmaxf((float)err, 1e-30f)));
+    return 0.9 / sqrt(sqrt(err));
+}
+
+template <typename real, bool kRamp, bool kKnots, int kMethod = COOP_RODAS4>
 __global__ void __launch_bounds__(COOP_BLOCK, PFR_COOP_MINB)
 rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     using namespace rodas4;
+    constexpr double kGamma = kMethod == COOP_ROS3 ? ros3::gamma : rodas4::gamma;
+    constexpr double kD1 = kMethod == COOP_ROS3 ? ros3::d1 : rodas4::d1;
     static_assert(!kRamp || kKnots, "a temperature ramp needs knot-limited stepping");
     __shared__ __align__(16) CoopParams<real> sp_block;
     CoopParams<real>& sp0 = sp_block;
@@ -358,12 +383,12 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
 #pragma unroll
                 for (int j = 0; j < NR; j++) s = fma(ldp(&sp.woutL[l][m][j]), gd[j], s);
                 fx[m] = s * slope;
-                ak1[m] = fma(h * real(d1), fx[m], ak1[m]);
+                ak1[m] = fma(h * real(kD1), fx[m], ak1[m]);
             }
         }
         {
             // rows of E for the lane's species: E[i][k] = delta_ik / (h gamma) - q_k sum_j (wout[i][j] g_j) nu[k][j]
-            const real fac = real(1.0 / gamma) * ih;
+            const real fac = real(1.0 / kGamma) * ih;
 #pragma unroll
             for (int m = 0; m < 3; m++) {
                 real G[NR];
@@ -415,69 +440,95 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
             for (int k = 0; k < NS; k++) Ainv[(m * NS + k) * COOP_BLOCK] = A[m][k];
         asm volatile("" ::: "memory");  // the inverse leaves the register file here
 #endif
-        // ---------------- six stages ----------------
-        real ak2[3], ak3[3], ak4[3], ak5[3], er[3], ynew[3], dy[3], g_[NS], q_[3];
+        // ---------------- stages ----------------
+        real er[3], ynew[3], dy[3], g_[NS], q_[3];
         coop_solve<real>(A, Ainv, ak1, base);
+        if constexpr (kMethod == COOP_ROS3) {
+            real ak2[3], ak3[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++) ynew[m] = y[m] + ak1[m];
+            if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + ros3::c2 * hs - tk), kT, mE, invT);
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const real s2 = fma(real(ros3::C21) * ih, ak1[m], dy[m]);
+                const real s3 = fma(real(ros3::C31) * ih, ak1[m], dy[m]);
+                ak2[m] = kRamp ? fma(h * real(ros3::d2), fx[m], s2) : s2;
+                ak3[m] = kRamp ? fma(h * real(ros3::d3), fx[m], s3) : s3;
+            }
+            coop_solve<real>(A, Ainv, ak2, base);
+#pragma unroll
+            for (int m = 0; m < 3; m++) ak3[m] = fma(real(ros3::C32) * ih, ak2[m], ak3[m]);
+            coop_solve<real>(A, Ainv, ak3, base);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                ynew[m] = fma(real(ros3::m3), ak3[m], fma(real(ros3::m2), ak2[m], ynew[m]));
+                er[m] = fma(real(ros3::e3), ak3[m], fma(real(ros3::e2), ak2[m], real(ros3::e1) * ak1[m]));
+            }
+        } else {
+            real ak2[3], ak3[3], ak4[3], ak5[3];
 
 #pragma unroll
-        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a21), ak1[m], y[m]);
-        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c2 * hs - tk), kT, mE, invT);
-        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+            for (int m = 0; m < 3; m++) ynew[m] = fma(real(a21), ak1[m], y[m]);
+            if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c2 * hs - tk), kT, mE, invT);
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
 #pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const real s = fma(real(C21) * ih, ak1[m], dy[m]);
-            ak2[m] = kRamp ? fma(h * real(d2), fx[m], s) : s;
+            for (int m = 0; m < 3; m++) {
+                const real s = fma(real(C21) * ih, ak1[m], dy[m]);
+                ak2[m] = kRamp ? fma(h * real(d2), fx[m], s) : s;
+            }
+            coop_solve<real>(A, Ainv, ak2, base);
+
+#pragma unroll
+            for (int m = 0; m < 3; m++) ynew[m] = fma(real(a32), ak2[m], fma(real(a31), ak1[m], y[m]));
+            if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c3 * hs - tk), kT, mE, invT);
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const real s = fma(real(C31) * ih, ak1[m], fma(real(C32) * ih, ak2[m], dy[m]));
+                ak3[m] = kRamp ? fma(h * real(d3), fx[m], s) : s;
+            }
+            coop_solve<real>(A, Ainv, ak3, base);
+
+#pragma unroll
+            for (int m = 0; m < 3; m++) ynew[m] = fma(real(a43), ak3[m], fma(real(a42), ak2[m], fma(real(a41), ak1[m], y[m])));
+            if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c4 * hs - tk), kT, mE, invT);
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const real s = fma(real(C41) * ih, ak1[m], fma(real(C42) * ih, ak2[m], fma(real(C43) * ih, ak3[m], dy[m])));
+                ak4[m] = kRamp ? fma(h * real(d4), fx[m], s) : s;
+            }
+            coop_solve<real>(A, Ainv, ak4, base);
+
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                ynew[m] = fma(real(a54), ak4[m], fma(real(a53), ak3[m], fma(real(a52), ak2[m], fma(real(a51), ak1[m], y[m]))));
+            if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + hs - tk), kT, mE, invT);
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                ak5[m] = fma(real(C51) * ih, ak1[m], fma(real(C52) * ih, ak2[m], fma(real(C53) * ih, ak3[m],
+                         fma(real(C54) * ih, ak4[m], dy[m]))));
+            coop_solve<real>(A, Ainv, ak5, base);
+
+#pragma unroll
+            for (int m = 0; m < 3; m++) ynew[m] += ak5[m];  // embedded 3rd-order solution
+            coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                er[m] = fma(real(C61) * ih, ak1[m], fma(real(C62) * ih, ak2[m], fma(real(C63) * ih, ak3[m],
+                        fma(real(C64) * ih, ak4[m], fma(real(C65) * ih, ak5[m], dy[m])))));
+            coop_solve<real>(A, Ainv, er, base);
+#pragma unroll
+            for (int m = 0; m < 3; m++) ynew[m] += er[m];
         }
-        coop_solve<real>(A, Ainv, ak2, base);
-
-#pragma unroll
-        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a32), ak2[m], fma(real(a31), ak1[m], y[m]));
-        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c3 * hs - tk), kT, mE, invT);
-        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const real s = fma(real(C31) * ih, ak1[m], fma(real(C32) * ih, ak2[m], dy[m]));
-            ak3[m] = kRamp ? fma(h * real(d3), fx[m], s) : s;
-        }
-        coop_solve<real>(A, Ainv, ak3, base);
-
-#pragma unroll
-        for (int m = 0; m < 3; m++) ynew[m] = fma(real(a43), ak3[m], fma(real(a42), ak2[m], fma(real(a41), ak1[m], y[m])));
-        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + c4 * hs - tk), kT, mE, invT);
-        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const real s = fma(real(C41) * ih, ak1[m], fma(real(C42) * ih, ak2[m], fma(real(C43) * ih, ak3[m], dy[m])));
-            ak4[m] = kRamp ? fma(h * real(d4), fx[m], s) : s;
-        }
-        coop_solve<real>(A, Ainv, ak4, base);
-
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-            ynew[m] = fma(real(a54), ak4[m], fma(real(a53), ak3[m], fma(real(a52), ak2[m], fma(real(a51), ak1[m], y[m]))));
-        if (kRamp) coop_arrhenius<real, false>(sp, p.inv_R, l, Tk + slope * real(t + hs - tk), kT, mE, invT);
-        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-            ak5[m] = fma(real(C51) * ih, ak1[m], fma(real(C52) * ih, ak2[m], fma(real(C53) * ih, ak3[m],
-                     fma(real(C54) * ih, ak4[m], dy[m]))));
-        coop_solve<real>(A, Ainv, ak5, base);
-
-#pragma unroll
-        for (int m = 0; m < 3; m++) ynew[m] += ak5[m];  // embedded 3rd-order solution
-        coop_rhs<real, false>(sp, p, l, base, kT, ynew, dy, g_, q_);
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-            er[m] = fma(real(C61) * ih, ak1[m], fma(real(C62) * ih, ak2[m], fma(real(C63) * ih, ak3[m],
-                    fma(real(C64) * ih, ak4[m], fma(real(C65) * ih, ak5[m], dy[m])))));
-        coop_solve<real>(A, Ainv, er, base);
 
         // ---------------- error estimate and step-size control (replicated, bit-identical in the 3 lanes) ----
         real e2 = real(0);
         bool fin_own = true;
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            ynew[m] += er[m];
             const real sk = atol + rtol * m_max(m_abs(y[m]), m_abs(ynew[m]));
             const real w = er[m] * fast_rcp<real>(sk);
             e2 = fma(w, w, e2);
@@ -489,9 +540,9 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
         finite = finite && (err == err) && (err < real(1e30));
 
         if (!done) {
-            nrhs += 6;
+            nrhs += kMethod == COOP_ROS3 ? 2 : 6;
             if (finite && err <= real(1)) {
-                double f = err > real(0) ? 0.9 / sqrt(sqrt((double)err)) : 6.0;
+                double f = err > real(0) ? ctrl_factor<kMethod>((double)err) : 6.0;
                 f = fmin(6.0, fmax(0.2, f));
                 hprop = clip ? fmax(hprop, hs * f) : hs * f;
                 nacc++;
@@ -524,7 +575,7 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
                 }
             } else {
                 nrej++;
-                const double f = finite ? fmax(0.2, 0.9 / sqrt(sqrt((double)err))) : 0.2;
+                const double f = finite ? fmax(0.2, ctrl_factor<kMethod>((double)err)) : 0.2;
                 hprop = hs * fmin(f, 0.9);
                 if (!(t + hprop > t) || hprop < 1e-300) { status = finite ? PFR_ST_UNDERFLOW_ : PFR_ST_NONFINITE_; done = true; }
             }

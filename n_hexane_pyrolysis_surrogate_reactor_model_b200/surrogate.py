@@ -29,7 +29,8 @@ TIME_IN_HI = (1150.0, 3.0e5, 1.0, 5.0)
 INFERENCE_CLAMPS = (1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # ...Eon_single_model.py:57-62
 TRAINING_WIDE_CLAMPS = (1.0e-6, 6.0e1, -1.0e1, 1.0e1, -1.0e5, 1.0e5)  # WIDE_Eoff_surrogate_model_training.py:39-53
 TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eoff_surrogate_model_training.py:40-43,54
-METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC}
+METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
+           "ros3": _lib.METHOD_ROS3}
 
 
 def _ptr(t):
