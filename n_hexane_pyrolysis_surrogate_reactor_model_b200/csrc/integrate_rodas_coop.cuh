@@ -331,10 +331,21 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
     }
     int kc = 0;
     double tk = t, tk1 = kKnots ? (double)a.tgrid[n + i] : t_final;
-    real Tk = real(a.T0[i]), slope = real(0);
+    real Tk = real(a.T0[i]), Tk1 = Tk, slope = real(0);
     if (kRamp) {
         Tk = real(a.Tprof[i]);
-        slope = (real(a.Tprof[n + i]) - Tk) / real(tk1 - tk);
+        Tk1 = real(a.Tprof[n + i]);
+        slope = (Tk1 - Tk) / real(tk1 - tk);
+    }
+    // knot k + 2 is fetched when the lane arrives at knot k and used one knot interval later: the (gathered, L2 / DRAM)
+    // load latency hides behind a whole step instead of stalling the group at every knot
+    // (RODAS4 on a ramp is at its register limit and measured 2 % slower with the two extra live values: it loads at the knot)
+    constexpr bool kAhead = kKnots && !(kMethod == COOP_RODAS4 && kRamp && sizeof(real) == 8);
+    float t_ahead = 0.f, T_ahead = 0.f;
+    if (kAhead) {
+        const size_t k2 = NTOT > 2 ? 2 : NTOT - 1;
+        t_ahead = a.tgrid[k2 * n + i];
+        if (kRamp) T_ahead = a.Tprof[k2 * n + i];
     }
     real kT[3], mE, invT;
     if (!kRamp) coop_arrhenius<real, false>(sp0, p.inv_R, l, Tk, kT, mE, invT);
@@ -561,10 +572,22 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
                             done = true;
                         } else {
                             tk = tk1;
-                            tk1 = (double)a.tgrid[(size_t)(kc + 1) * n + i];
-                            if (kRamp) {
-                                Tk = real(a.Tprof[(size_t)kc * n + i]);
-                                slope = (real(a.Tprof[(size_t)(kc + 1) * n + i]) - Tk) / real(tk1 - tk);
+                            if (kAhead) {
+                                tk1 = (double)t_ahead;
+                                const size_t k2 = (size_t)(kc + 2 < NTOT ? kc + 2 : NTOT - 1);
+                                t_ahead = a.tgrid[k2 * n + i];
+                                if (kRamp) {
+                                    Tk = Tk1;
+                                    Tk1 = real(T_ahead);
+                                    slope = (Tk1 - Tk) / real(tk1 - tk);
+                                    T_ahead = a.Tprof[k2 * n + i];
+                                }
+                            } else {
+                                tk1 = (double)a.tgrid[(size_t)(kc + 1) * n + i];
+                                if (kRamp) {
+                                    Tk = real(a.Tprof[(size_t)kc * n + i]);
+                                    slope = (real(a.Tprof[(size_t)(kc + 1) * n + i]) - Tk) / real(tk1 - tk);
+                                }
                             }
                         }
                     } else {

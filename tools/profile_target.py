@@ -1,5 +1,5 @@
 """Small fixed workload for ncu captures: one Eon integrate, one Eoff integrate, the three MLP passes.
-Usage: python tools/profile_target.py [n] [precision]"""
+Usage: python tools/profile_target.py [n] [precision] [method] [tol]"""
 import os
 import sys
 
@@ -15,12 +15,14 @@ from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import lhs_conditions
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     prec = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    method = sys.argv[3] if len(sys.argv) > 3 else "rodas4"
+    tol = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-6
     gold = os.path.join(ROOT, "tests", "golden", "containers", "LLNL.npz")
     T, P, L, U = (torch.as_tensor(a).cuda() for a in lhs_conditions(n, seed=13895))
     on = Surrogate(ModelSet.from_packed(gold, "Eon"))
     off = Surrogate(ModelSet.from_packed(gold, "Eoff"))
     for _ in range(2):
-        r1 = on.sweep(T, P, L, U, precision=prec)
+        r1 = on.sweep(T, P, L, U, precision=prec, method=method, rtol=tol, atol=tol)
         r2 = off.sweep(T, P, L, U, precision=prec)
     torch.cuda.synchronize()
     print("ok", float(r1.y.sum()), float(r2.y.sum()), int(r1.status.sum()), int(r2.status.sum()))
