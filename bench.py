@@ -7,11 +7,12 @@
 One "step" = one pass of the surrogate hot path over one batch of 2^20 conditions per GPU (weak scaling):
 inlet concentration -> temperature MLP + time MLPs -> enforce_strict / idx_cut -> adaptive Rosenbrock
 integration -> outlet species [9, n] (+ the final gather when N > 1).  Headline workload: LLNL Eon (the
-coupled CRNN + temperature-profile MLP path), float64 state.  Integrator of the headline: the 3-stage Rosenbrock
-method (ROS3) at rtol = atol = 1e-7, which on this knot-limited path is as close to the converged solution as the
-6-stage RODAS4 at the reference's 1e-6 (both errors are measured in the run and reported under "accuracy"; RODAS4 at
-1e-6 is timed under "variants").  The LLNL Eoff (isothermal) sweep, where RODAS4 at 1e-6 is the better choice, is
-timed as well and reported under "variants".
+coupled CRNN + temperature-profile MLP path), float64 state.  Integrator of the headline: the explicit knot-limited
+fast path (BS23, one step per knot interval of the MLP grid; conditions it flags as stiff fall back to the Rosenbrock
+kernel) at a tolerance tight enough that its outlet error is below that of the 6-stage Rosenbrock method RODAS4 at the
+reference's 1e-6 -- all errors are measured in the run and reported under "accuracy"; the Rosenbrock methods (ROS3 at
+1e-7, RODAS4 at 1e-6) are timed under "variants".  The LLNL Eoff (isothermal, free-stepping) sweep, where RODAS4 at
+1e-6 is the better choice, is timed as well and reported under "variants".
 """
 from __future__ import annotations
 
@@ -39,6 +40,8 @@ FP64_RHS = 2 * 81 + 9 * FP64_LOG + 9 * FP64_EXP + 27           # two 9x9 mat-vec
 FP64_RHS_T = FP64_LOG + FP64_RCP + 27                          # on a T ramp: ln T, 1/T, kT_j = lnA - Ea/RT + b lnT
 FP64_STEP = (81 + 729 + 81) + (204 + 36 + 9 * FP64_RCP) + 6 * 81 + (90 + 18 + 135 + 15) + 50   # J, LU, 6 solves, stage sums, norm
 FP64_STEP_ROS3 = (81 + 729 + 81) + (204 + 36 + 9 * FP64_RCP) + 3 * 81 + 108 + 50                # J, LU, 3 solves, stage sums, norm
+FP64_STEP_BS23 = 18 + 36 + 27 + 18 + 63                                                        # stage arguments, solution, error combination, norm
+STEP_INSTR = {"rodas4": FP64_STEP, "ros3": FP64_STEP_ROS3, "bs23": FP64_STEP_BS23}
 
 
 class ClockSampler:
@@ -89,7 +92,7 @@ def _flops(stats, energy_on, method="rodas4"):
     """Algorithmic FP64 work of one integrator launch from its per-trajectory counters [3, n]."""
     import torch
     acc, rej, rhs = (stats[i].to(torch.float64).sum().item() for i in range(3))
-    instr = rhs * (FP64_RHS + (FP64_RHS_T if energy_on else 0)) + (acc + rej) * (FP64_STEP_ROS3 if method == "ros3" else FP64_STEP)
+    instr = rhs * (FP64_RHS + (FP64_RHS_T if energy_on else 0)) + (acc + rej) * STEP_INSTR[method]
     return 2.0 * instr, {"accepted_mean": acc / stats.shape[1], "rejected_mean": rej / stats.shape[1], "rhs_mean": rhs / stats.shape[1]}
 
 
@@ -148,10 +151,12 @@ def run_ours(args):
     peaks = measure_peaks() if rank == 0 else None
     result, variants = None, {}
     accuracy = None
-    for variant, mlp_mode, method in (("Eon", "tf32x3", "ros3"), ("Eoff", "tf32x3", "rodas4"), ("Eon", "tf32x3", "rodas4"), ("Eon", "fp32", "ros3")):
+    tols = {"bs23": args.bs23_tol, "ros3": args.ros3_tol}
+    for variant, mlp_mode, method in (("Eon", "tf32x3", "bs23"), ("Eoff", "tf32x3", "rodas4"), ("Eon", "tf32x3", "ros3"), ("Eon", "tf32x3", "rodas4"),
+                                      ("Eon", "fp32", "bs23")):
         sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), variant), device=dev, mlp_mode=mlp_mode)
-        headline = variant == "Eon" and mlp_mode == "tf32x3" and method == "ros3"
-        rtol, atol = (args.ros3_tol, args.ros3_tol) if method == "ros3" else (args.rtol, args.atol)
+        headline = variant == "Eon" and mlp_mode == "tf32x3" and method == "bs23"
+        rtol, atol = (tols[method], tols[method]) if method in tols else (args.rtol, args.atol)
         kw = dict(method=method, precision=args.precision, rtol=rtol, atol=atol)
 
         def step_device():
@@ -185,7 +190,7 @@ def run_ours(args):
             c0 = sur.inlet_concentration(T, P)
             tend = res.t_end
             kern = lambda: sur.integrate(T, c0, t_end=tend, perm=perm, **kw)
-        kms, _, _ = time_steps(kern, 3, 1)
+        kms, _, _ = time_steps(kern, 3, 2)
         kms /= 3
         if headline and rank == 0:
             # outlet deviation from the tight-tolerance solution of the same kernel family (its parity with the converged
@@ -197,7 +202,8 @@ def run_ours(args):
             scale = torch.clamp(yref.abs(), min=1e-3)
             accuracy = {"reference_solution": "RODAS4 at rtol = atol = 1e-11 on the same grids", "conditions": int(sel.numel()),
                         "error": "max over species of |y - y_ref| / max(|y_ref|, 1e-3 mol/m3) at the outlet"}
-            for nm, k2 in (("headline_ros3", dict(method="ros3", rtol=rtol, atol=atol)),
+            for nm, k2 in (("headline_bs23", dict(method="bs23", rtol=rtol, atol=atol)),
+                           ("ros3", dict(method="ros3", rtol=args.ros3_tol, atol=args.ros3_tol)),
                            ("rodas4_at_reference_tolerances", dict(method="rodas4", rtol=args.rtol, atol=args.atol))):
                 e = ((sub(**k2) - yref).abs() / scale).amax(0)
                 accuracy[nm] = {"rtol": k2["rtol"], "atol": k2["atol"], "max": float(e.max()), "p99": float(torch.quantile(e, 0.99)),
@@ -207,7 +213,7 @@ def run_ours(args):
             "value": n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps,
             "e2e": n_total * steps / (ms_e2e * 1e-3), "failed_trajectories": bad, "work_per_trajectory": work,
             "integrator_ms": kms, "integrator_share_of_step": kms / (ms / steps),
-            "integrator_fp64_tflops": flops / (kms * 1e-3) / 1e12,
+            "integrator_fp64_tflops": flops / (kms * 1e-3) / 1e12, "stiff_fallbacks": int(getattr(res, "stiff_fallbacks", 0)),
         }
         entry["mlp_arithmetic"] = mlp_mode
         entry["integrator"], entry["rtol"], entry["atol"] = method, rtol, atol
@@ -218,11 +224,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # the other mechanisms of config 3 and the reference-behaviour integrator, device-resident timing only
-    for mech, variant, method, prec in (("JetSurf", "Eon", "ros3", 64), ("JetSurf", "Eoff", "rodas4", 64), ("NUIG", "Eon", "ros3", 64),
+    for mech, variant, method, prec in (("JetSurf", "Eon", "bs23", 64), ("JetSurf", "Eoff", "rodas4", 64), ("NUIG", "Eon", "bs23", 64),
                                         ("NUIG", "Eoff", "rodas4", 64), ("LLNL", "Eoff", "dopri5", 32), ("LLNL", "Eon", "rodas4", 32)):
         sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, f"{mech}.npz"), variant), device=dev)
-        tol2 = args.ros3_tol if method == "ros3" else args.rtol
-        kw2 = dict(method=method, precision=prec, rtol=tol2, atol=tol2 if method == "ros3" else args.atol)
+        tol2 = tols.get(method, args.rtol)
+        kw2 = dict(method=method, precision=prec, rtol=tol2, atol=tol2 if method in tols else args.atol)
         ms, res, _ = time_steps(lambda: gather_outlets(sur.sweep(T, P, L, U, **kw2).y, n_total), 2, 1)
         r = sur.sweep(T, P, L, U, **kw2)
         name = f"{mech}_{variant}" + ("" if prec == 64 else f"_{method}_f{prec}")
@@ -244,25 +250,27 @@ def run_ours(args):
         "config": {"workload": "LLNL Eon CRNN + LLNL_2D temperature MLP + LLNL_4D_time_on MLP; 4-D Latin hypercube "
                                "(T 870-1150 K, P 1-3 bar, L 0.5-1 m, u0 2.5-5 m/s), scipy qmc seed 13895",
                    "conditions_per_gpu": args.conditions_per_gpu, "conditions_total": n_total,
-                   "integrator": "ros3: adaptive 3-stage L-stable Rosenbrock 3(2), analytic Jacobian, knot-limited steps (PFR_METHOD_ROS3); "
-                                 "run at a 10x tighter tolerance than the reference's 1e-6 so that its outlet error is no larger than "
-                                 "RODAS4's at 1e-6 (see accuracy; RODAS4 at 1e-6 is timed under variants.LLNL_Eon_rodas4)",
+                   "integrator": "bs23: explicit Bogacki-Shampine 3(2), adaptive, knot-limited steps, one thread per condition (PFR_METHOD_BS23), "
+                                 "Rosenbrock (ROS3) fallback for conditions flagged stiff; run at a tighter tolerance than the reference's "
+                                 "1e-6 so that its outlet error is below RODAS4's at 1e-6 (see accuracy; the Rosenbrock methods are timed "
+                                 "under variants.LLNL_Eon_ros3 / LLNL_Eon_rodas4)",
                    "mlp_arithmetic": "tcgen05 tensor cores, error-compensated 3xTF32 split, four float32 TMEM accumulators per tile "
                                      "(float32-accurate: 1.3e-6 vs torch CPU float32; the FP32-FFMA path is timed under variants)",
-                   "rtol": args.ros3_tol, "atol": args.ros3_tol, "weights": "trained reference containers (tests/golden/containers)",
+                   "rtol": args.bs23_tol, "atol": args.bs23_tol, "weights": "trained reference containers (tests/golden/containers)",
                    "l2": "per-step working set (6.4 KB of grids per condition, 6.7 GB per GPU) exceeds the 126 MB L2",
                    "parallelism": f"conditions sharded over {world} rank(s); final all-gather of [9,n] outlets only"},
         "e2e": {"value": e["e2e"], "unit": "trajectories/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (72 if args.precision == 64 else 36) * n + 4 * n,
                 "api": "Surrogate.sweep_host (numpy in, numpy out; per rank: its shard of conditions in, its outlets + status out)"},
         "gpu_launches": int(result["launches"]),
         "clocks": result["clk"],
-        "roofline": {"bound": "fp64_pipe", "kernel": "rodas4_coop_kernel<double,ramp,knots,ROS3>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
+        "roofline": {"bound": "fp64_pipe", "kernel": "bs23_kernel<double,ramp>", "achieved": result["flops"] / (result["kms"] * 1e-3) / 1e12,
                      "peak": peak / 1e12, "unit": "TFLOP/s", "frac": result["flops"] / (result["kms"] * 1e-3) / peak,
                      "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
                      "kernel_ms": result["kms"], "kernel_share_of_step": e["integrator_share_of_step"],
-                     "traffic": 23.5e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01b_ncu_full_rodas4_coop_fp64.txt: 23.5 KB per condition x n",
+                     "traffic": 51.8e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01g_ncu_full_bs23_fp64.txt: 51.8 KB per condition x n "
+                                                                "(the two [801][n] float32 grids are gathered through the cost-sort permutation: one 32-byte sector per 4-byte knot value)",
                      "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
-                                   f"ROS3 step overhead {FP64_STEP_ROS3} (Jacobian, LU, 3 solves, stage sums; RODAS4: {FP64_STEP}); see DESIGN.md"},
+                                   f"BS23 step overhead {FP64_STEP_BS23} (stage sums, error norm; ROS3: {FP64_STEP_ROS3}, RODAS4: {FP64_STEP}); see DESIGN.md"},
         "accuracy": accuracy,
         "peaks_measured": {"ffma_tflops": peaks["ffma_flops"] / 1e12, "dfma_tflops": peaks["dfma_flops"] / 1e12, "mufu_tops": peaks["mufu_ops"] / 1e12},
         "variants": variants,
@@ -372,7 +380,8 @@ def main():
     ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
     ap.add_argument("--rtol", type=float, default=1e-6)
     ap.add_argument("--atol", type=float, default=1e-6)
-    ap.add_argument("--ros3-tol", type=float, default=1e-7, help="rtol = atol of the 3-stage method on the Eon path")
+    ap.add_argument("--ros3-tol", type=float, default=1e-7, help="rtol = atol of the 3-stage Rosenbrock method on the Eon path")
+    ap.add_argument("--bs23-tol", type=float, default=1e-8, help="rtol = atol of the explicit fast path on the Eon path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

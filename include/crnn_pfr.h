@@ -32,6 +32,8 @@ extern "C" {
 #define PFR_ST_MAXSTEPS 1
 #define PFR_ST_NONFINITE 2
 #define PFR_ST_UNDERFLOW 3
+#define PFR_ST_STIFF 4      /* PFR_METHOD_BS23 only: the explicit fast path met a stiff knot interval; integrate this condition with
+                            * PFR_METHOD_ROS3 / PFR_METHOD_RODAS4 (Surrogate does so automatically) */
 
 #define PFR_FLAG_DENSE_RAW 1
 
@@ -41,6 +43,9 @@ extern "C" {
 #define PFR_METHOD_ROS3 3       /* 3-stage L-stable Rosenbrock of order 3(2), 2 right-hand sides per step, same kernel structure
                                  * as PFR_METHOD_RODAS4: cheaper per knot-limited step, needs a ~10x tighter tolerance for the
                                  * same accuracy (work-precision table) */
+#define PFR_METHOD_BS23 4       /* explicit Bogacki-Shampine 3(2), one thread per condition, knot-limited (tgrid required): the
+                                 * fast path for the non-stiff knot intervals of the coupled (Eon) path; a condition that turns
+                                 * out stiff stops with PFR_ST_STIFF */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;

@@ -13,7 +13,10 @@ METHOD_RODAS4 = 0
 METHOD_DOPRI5 = 1
 METHOD_RODAS4_TPC = 2
 METHOD_ROS3 = 3
-STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow"}
+METHOD_BS23 = 4
+ST_STIFF = 4
+STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow",
+               4: "stiff for the explicit fast path (integrate with ros3 / rodas4)"}
 
 c_void_p, c_int, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -12,7 +12,9 @@
 #include "crnn_device.cuh"
 #include "integrate_dopri5.cuh"
 #include "integrate_rodas.cuh"
+#include "integrate_bs23.cuh"
 #include "integrate_rodas_coop.cuh"
+#include "integrate_bs23.cuh"
 #include "adjoint.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
@@ -498,6 +500,30 @@ static int dispatch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cu
     return launch_rodas_coop<real, false, false, kMethod>(p, a, st);
 }
 
+// work-queue counters of bs23_kernel: a small ring so that launches in flight on different streams do not share one
+static int* g_bs23_counters = nullptr;
+static int g_bs23_next = 0, g_num_sms = 0;
+constexpr int BS23_COUNTER_RING = 64;
+
+template <typename real>
+static int dispatch_bs23(const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
+    if (!g_bs23_counters) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaMalloc(&g_bs23_counters, BS23_COUNTER_RING * sizeof(int)));
+    }
+    RodasArgs a = a0;
+    a.work_counter = g_bs23_counters + (g_bs23_next++ % BS23_COUNTER_RING);
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+    const int full = (a.n + BS23_BLOCK - 1) / BS23_BLOCK, persistent = BS23_CTAS_PER_SM * g_num_sms;
+    const int grid = full < persistent ? full : persistent;
+    if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, 0, st>>>(p, a);
+    else bs23_kernel<real, false><<<grid, BS23_BLOCK, 0, st>>>(p, a);
+    CK_LAUNCH("bs23_kernel");
+    return PFR_OK;
+}
+
 template <typename real>
 static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaStream_t st) {
     const int grid = (a.n + DOPRI_BLOCK - 1) / DOPRI_BLOCK;
@@ -513,7 +539,8 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
-    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 && method != PFR_METHOD_BS23) return PFR_EINVAL;
+    if (method == PFR_METHOD_BS23 && !tgrid) return PFR_EINVAL;   // the explicit fast path is the knot-limited stepper
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
@@ -530,6 +557,10 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (method == PFR_METHOD_ROS3) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
         return precision == 64 ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
+    }
+    if (method == PFR_METHOD_BS23) {
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
+        return precision == 64 ? dispatch_bs23<double>(m->pd, a, st) : dispatch_bs23<float>(m->pf, a, st);
     }
     if (method == PFR_METHOD_RODAS4_TPC) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};

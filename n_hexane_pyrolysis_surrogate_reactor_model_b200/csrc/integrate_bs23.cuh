@@ -1,0 +1,366 @@
+// Explicit knot-limited integrator for the NON-STIFF regime of the CRNN plug-flow problem: Bogacki-Shampine 3(2)
+// with FSAL, one PFR condition per thread.
+//
+// Why it exists.  On the coupled (Eon) path the temperature is the MLP's piecewise-linear profile and a step never
+// crosses one of its 801 knots (integrate_rodas.cuh explains why).  The knot spacing (median 5e-4 s) is then 10-50x
+// SMALLER than the step an explicit method could take stably: the reference's own dopri5 needs 8-55 accepted steps
+// for a whole trajectory (tests/golden/reference_vectors.npz, Eon/dopri5_stats), so h * rho(J) << 1 on every knot
+// interval.  A Rosenbrock step pays for a 9x9 Jacobian and its inverse (half of its FP64 work) that buy nothing
+// there.  One BS23 step per knot interval is three right-hand sides and nothing else: 2.4x less FP64 work per
+// trajectory than ROS3 at the same accuracy (work-precision table).
+//
+// Why one thread per condition here (the Rosenbrock kernels use three lanes).  Without the Jacobian the live state is
+// four 9-vectors; it fits in registers, there are no shuffles at all, every thread has nine independent log / exp /
+// dot-product chains in flight, and a warp instruction serves 32 conditions instead of 10.  The CRNN coefficients are
+// broadcast reads from a block-shared copy (two per 16-byte load).
+//
+// Stiffness guard.  The embedded error estimate of an explicit pair blows up when h * lambda leaves the stability
+// region, so a stiff interval shows up as a cascade of rejected sub-steps.  A condition that needs more than
+// 8 attempts per knot interval on average (+ 512) stops with status PFR_ST_STIFF; the host (Surrogate) then integrates
+// exactly those conditions with the Rosenbrock kernel.  (An accuracy-limited explicit run takes 1.0-1.6 attempts per
+// interval at rtol = atol = 1e-5 ... 1e-9 and ~3.5 at 1e-10; error control holds either way, the guard only bounds the
+// wasted work: at most ~3x the cost of the Rosenbrock integration it falls back to.)  The
+// product stays an adaptive stiff-capable integrator; this is its fast path.
+//
+// Same controller conventions as the Rosenbrock kernels: RMS norm against atol + rtol max(|y0|, |y1|), Hairer-style
+// first step, factor clip(0.9 err^(-1/3), 0.2, 6), a knot-clipped accepted step does not shrink the proposal.
+#pragma once
+#include "crnn_device.cuh"
+#include "fastmath.cuh"
+#include "integrate_rodas.cuh"
+
+namespace pfr {
+
+constexpr int BS23_BLOCK = 128;
+constexpr int BS23_CTAS_PER_SM = 2;   // persistent grid: 255 registers x 128 threads, two CTAs fill the register file
+constexpr int PFR_ST_STIFF_ = 4;
+#ifndef PFR_BS23_MINB
+#define PFR_BS23_MINB 2   // 255 registers, 8 warps / SM: measured 11 % faster than 168 registers with spills
+#endif
+
+template <typename real> __device__ __forceinline__ real t_log(real x, const FastTables& ft);
+template <> __device__ __forceinline__ double t_log<double>(double x, const FastTables& ft) { return fast_log(x, ft.logtab); }
+template <> __device__ __forceinline__ float t_log<float>(float x, const FastTables&) { return logf(x); }
+template <typename real> __device__ __forceinline__ real t_exp(real x, const FastTables& ft);
+template <> __device__ __forceinline__ double t_exp<double>(double x, const FastTables& ft) { return fast_exp(x, ft.exptab); }
+template <> __device__ __forceinline__ float t_exp<float>(float x, const FastTables&) { return expf(x); }
+
+// 1/x to ~1e-10 (MUFU.RCP64H seed + one Newton step): enough for the weights of the error norm
+__device__ __forceinline__ double rcp_norm(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ float rcp_norm(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double rcp_full(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float rcp_full(float x) { return __frcp_rn(x); }
+
+// Block-shared copy of the CRNN coefficients, laid out in the order the right-hand side consumes them.  Every thread
+// reads the same address (a broadcast), two coefficients per 16-byte load.  (As FMA operands straight from the
+// constant bank they would have to pass through uniform registers on sm_100: 189 64-bit values do not fit, and the
+// compiler spills uniform registers into vector registers and back -- measured: 25 % of the instruction stream.)
+template <typename real>
+struct TpcCoef {
+    real arr[NR][4];      // Ea_j, b_j, lnA_j, 0
+    real nu[NS][10];      // nu[k][j], j = 0..8, 0
+    real woutT[NR][10];   // wout[i][j] stored [j][i], i = 0..8, 0
+    FastTables ft;
+};
+
+// volatile: the values are loop-invariant; a plain load lets the compiler hoist all of them out of the step loop.  `after`
+// is an artificial input: the load may not be scheduled before that value exists, which keeps the nine coefficient rows
+// of a mat-vec from being fetched (and held in 180 registers) ahead of the logarithms / exponentials they multiply.
+__device__ __forceinline__ void lds2(const double* q, double& a, double& b, double after) {
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned)__cvta_generic_to_shared(q)), "d"(after));
+}
+__device__ __forceinline__ void lds2(const float* q, float& a, float& b, float after) {
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"((unsigned)__cvta_generic_to_shared(q)), "f"(after));
+}
+template <typename real>
+__device__ __forceinline__ void lds9(const real* q, real (&c)[10], real after) {
+#pragma unroll
+    for (int e = 0; e < 5; e++) lds2(q + 2 * e, c[2 * e], c[2 * e + 1], after);
+}
+
+// conservative |x| >= bound test on the high word (double) so that it runs on the integer pipe; `thr` = bound_key(bound)
+__device__ __forceinline__ int bound_key(double b) { return __double2hiint(fabs(b)); }
+__device__ __forceinline__ int bound_key(float b) { return __float_as_int(fabsf(b)); }
+__device__ __forceinline__ bool maybe_outside(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) >= thr; }
+__device__ __forceinline__ bool maybe_outside(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) >= thr; }
+
+// du = f(T, y): streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
+// min(|zlo|, |zhi|) and min(|dulo|, |duhi|): the exponent and output clamps are skipped when no entry comes near them.
+template <typename real>
+__device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, real T,
+                                        const real (&y)[NS], real (&du)[NS]) {
+    real z[NR];
+    {
+        const real invT = rcp_full(T);
+        const real mE = -p.inv_R * invT;
+        const real lnT = t_log<real>(T, sc.ft);
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            real Ea, b, lnA, pad;
+            lds2(&sc.arr[j][0], Ea, b, lnT);
+            lds2(&sc.arr[j][2], lnA, pad, lnT);
+            z[j] = fma(Ea, mE, fma(b, lnT, lnA));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        const real l = t_log<real>(m_min(m_max(y[k], p.lb), p.ub), sc.ft);
+        real c[10];
+#ifdef BS_CONSTBANK
+#pragma unroll
+        for (int j = 0; j < NR; j++) c[j] = p.nu[k][j];
+#else
+        lds9(sc.nu[k], c, l);
+#endif
+#pragma unroll
+        for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
+    }
+    bool near = false;
+#pragma unroll
+    for (int j = 0; j < NR; j++) near = near || maybe_outside(z[j], zthr);
+#ifdef BS_NOBRANCH
+    near = true;
+#endif
+    if (near) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) z[j] = m_min(m_max(z[j], p.zlo), p.zhi);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) du[i] = real(0);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const real r = t_exp<real>(z[j], sc.ft);
+        real c[10];
+#ifdef BS_CONSTBANK
+#pragma unroll
+        for (int i = 0; i < NS; i++) c[i] = p.wout[i][j];
+#else
+        lds9(sc.woutT[j], c, r);
+#endif
+#pragma unroll
+        for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
+    }
+    near = false;
+#pragma unroll
+    for (int i = 0; i < NS; i++) near = near || maybe_outside(du[i], dthr);
+#ifdef BS_NOBRANCH
+    near = true;
+#endif
+    if (near) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) du[i] = m_min(m_max(du[i], p.dulo), p.duhi);
+    }
+}
+
+template <typename real, bool kRamp>
+__global__ void __launch_bounds__(BS23_BLOCK, PFR_BS23_MINB)
+bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+    __shared__ __align__(16) TpcCoef<real> sc;
+    for (int e = threadIdx.x; e < NS * 10; e += BS23_BLOCK) {
+        const int r = e / 10, c = e % 10;
+        sc.nu[r][c] = c < NR ? p.nu[r][c] : real(0);
+        sc.woutT[r][c] = c < NS ? p.wout[c][r] : real(0);
+    }
+    if (threadIdx.x < NR) {
+        sc.arr[threadIdx.x][0] = p.Ea[threadIdx.x];
+        sc.arr[threadIdx.x][1] = p.b[threadIdx.x];
+        sc.arr[threadIdx.x][2] = p.lnA[threadIdx.x];
+        sc.arr[threadIdx.x][3] = real(0);
+    }
+    if (sizeof(real) == 8) {
+        for (int e = threadIdx.x; e < LOGTAB_N; e += BS23_BLOCK) sc.ft.logtab[e] = a.tables->logtab[e];
+        for (int e = threadIdx.x; e < EXPTAB_N; e += BS23_BLOCK) sc.ft.exptab[e] = a.tables->exptab[e];
+    }
+    __syncthreads();
+    const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)a.n;
+    real* __restrict__ y_out = static_cast<real*>(a.y_out);
+    real* __restrict__ y_dense = static_cast<real*>(a.y_dense);
+    const bool dense = y_dense != nullptr;
+    const bool raw = (a.flags & 1) != 0;
+    const real rtol = real(a.rtol), atol = real(a.atol);
+
+    // Lane-level work queue.  Conditions take different numbers of steps (sub-steps in the fast phases, different outlet
+    // knots), so with a fixed condition per lane a warp idles a quarter of its lanes on average (measured: 23.6 of 32
+    // active).  Instead every lane that finishes draws the next condition from a global counter (one atomic per warp and
+    // round) and carries on inside the same loop; the grid is persistent (BS23_CTAS_PER_SM CTAs per SM).  A new
+    // condition enters with a zero-length step: with h = 0 all stages evaluate f(t0, y0), so the ordinary step code
+    // produces the FSAL slope k1 and no second copy of the right-hand side is needed.
+    bool have = false, fresh = false, exhausted = false;
+    int i = 0, kend = 0, kc = 0, nacc = 0, nrej = 0, nrhs = 0, status = 0, stiff_cap = 0;
+    double t = 0.0, t_final = 0.0, tk = 0.0, tk1 = 0.0, hprop = 0.0;
+    real Tk = real(0), Tk1 = real(0), slope = real(0);
+    float t_ahead = 0.f, T_ahead = 0.f;
+    real y[NS], k1[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) { y[k] = real(0); k1[k] = real(0); }
+
+    while (true) {
+        const unsigned want = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (want) {
+            int base = 0;
+            const int leader = __ffs(want) - 1;
+            if (lane == leader) base = atomicAdd(a.work_counter, __popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have && !exhausted) {
+                const int slot = base + __popc(want & ((1u << lane) - 1u));
+                if (slot >= a.n) {
+                    exhausted = true;
+                } else {
+                    i = a.perm ? a.perm[slot] : slot;
+                    kend = a.idx_end ? a.idx_end[i] : NTOT - 1;
+#pragma unroll
+                    for (int k = 0; k < NS; k++) { y[k] = real(0); k1[k] = real(0); }   // (k1 is multiplied by h = 0 in the entry step)
+                    y[NS - 3] = real(a.c0[i]);
+                    t = (double)a.tgrid[i];
+                    t_final = (double)a.tgrid[(size_t)kend * n + i];
+                    kc = 0;
+                    tk = t;
+                    tk1 = (double)a.tgrid[n + i];
+                    Tk = Tk1 = real(a.T0[i]);
+                    slope = real(0);
+                    if (kRamp) {
+                        Tk = real(a.Tprof[i]);
+                        Tk1 = real(a.Tprof[n + i]);
+                        slope = (Tk1 - Tk) / real(tk1 - tk);
+                    }
+                    // knot k + 2 is fetched on arrival at knot k and used one interval later (hides the gathered-load latency)
+                    const size_t k2i = NTOT > 2 ? 2 : NTOT - 1;
+                    t_ahead = a.tgrid[k2i * n + i];
+                    T_ahead = kRamp ? a.Tprof[k2i * n + i] : 0.f;
+                    nacc = nrej = nrhs = status = 0;
+                    stiff_cap = 8 * kend + 512;
+                    hprop = 0.0;
+                    if (dense) {
+#pragma unroll
+                        for (int k = 0; k < NS; k++) y_dense[(size_t)k * n + i] = raw ? y[k] : m_min(m_max(y[k], p.lb), p.ub);
+                    }
+                    have = true;
+                    fresh = (kend != 0) && (t_final > t);
+                    if (!fresh) kc = -1;   // nothing to integrate: falls through to the output code below
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !have)) break;
+        bool done = have && !fresh && kc < 0;
+        if (have && !done) {
+            const double dist = tk1 - t;
+            const bool clip = !fresh && hprop * 1.01 >= dist;
+            const double hs = fresh ? 0.0 : (clip ? dist : hprop);
+            const real h = real(hs);
+            const real tau = real(t - tk);   // time since the knot: T(t + c h) = Tk + slope (tau + c h)
+            real k2[NS], k3[NS], w[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) w[k] = fma(real(0.5) * h, k1[k], y[k]);
+            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? fma(slope, fma(real(0.5), h, tau), Tk) : Tk, w, k2);
+#pragma unroll
+            for (int k = 0; k < NS; k++) w[k] = fma(real(0.75) * h, k2[k], y[k]);
+            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? fma(slope, fma(real(0.75), h, tau), Tk) : Tk, w, k3);
+            // third-order solution; k2, k3 fold into the error combination and die here
+            real er[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                w[k] = fma(h, fma(real(4.0 / 9.0), k3[k], fma(real(1.0 / 3.0), k2[k], real(2.0 / 9.0) * k1[k])), y[k]);
+                er[k] = fma(real(1.0 / 9.0), k3[k], fma(real(1.0 / 12.0), k2[k], real(-5.0 / 72.0) * k1[k]));
+            }
+            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? (clip ? Tk1 : fma(slope, tau + h, Tk)) : Tk, w, k2);   // k4 = f(t + h, y1): next k1
+            nrhs += 3;
+            real e2 = real(0), d0 = real(0), d1 = real(0);
+            bool finite = true;
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                const real ek = h * fma(real(-1.0 / 8.0), k2[k], er[k]);
+                const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
+                e2 = fma(ek * isk, ek * isk, e2);
+                d0 = fma(y[k] * isk, y[k] * isk, d0);     // only used by a fresh condition (first-step guess)
+                d1 = fma(k2[k] * isk, k2[k] * isk, d1);
+                finite = finite && (m_abs(w[k]) < real(1e30));
+            }
+            const real err = m_sqrt<real>(e2 / real(NS));
+            finite = finite && (err == err) && (err < real(1e30));
+            const float fac = 0.9f / cbrtf(fmaxf((float)err, 1e-30f));
+            if (fresh) {
+                // the zero-length step left y unchanged and k2 = f(t0, y0); Hairer-style first step from |y0| and |f0|
+#pragma unroll
+                for (int k = 0; k < NS; k++) k1[k] = k2[k];
+                d0 = m_sqrt<real>(d0 / real(NS));
+                d1 = m_sqrt<real>(d1 / real(NS));
+                const double h0 = (d0 < real(1e-5) || d1 < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
+                hprop = fmin(100.0 * h0, t_final - t);
+                fresh = false;
+            } else if (finite && err <= real(1)) {
+                const double f = fmin(6.0, fmax(0.2, (double)fac));
+                hprop = clip ? fmax(hprop, hs * f) : hs * f;
+                nacc++;
+#pragma unroll
+                for (int k = 0; k < NS; k++) { y[k] = w[k]; k1[k] = k2[k]; }
+                if (clip) {
+                    t = tk1;
+                    kc++;
+                    if (dense) {
+#pragma unroll
+                        for (int k = 0; k < NS; k++) y_dense[((size_t)kc * NS + k) * n + i] = raw ? y[k] : m_min(m_max(y[k], p.lb), p.ub);
+                    }
+                    if (kc >= kend) {
+                        done = true;
+                    } else {
+                        tk = tk1;
+                        tk1 = (double)t_ahead;
+                        const size_t kk = (size_t)(kc + 2 < NTOT ? kc + 2 : NTOT - 1);
+                        t_ahead = a.tgrid[kk * n + i];
+                        if (kRamp) {
+                            Tk = Tk1;
+                            Tk1 = real(T_ahead);
+                            slope = (Tk1 - Tk) / real(tk1 - tk);
+                            T_ahead = a.Tprof[kk * n + i];
+                        }
+                    }
+                } else {
+                    t += hs;
+                }
+            } else {
+                nrej++;
+                const double f = finite ? fmax(0.2, (double)fac) : 0.2;
+                hprop = hs * fmin(f, 0.9);
+                if (!(t + hprop > t) || hprop < 1e-300) { status = finite ? PFR_ST_UNDERFLOW_ : PFR_ST_NONFINITE_; done = true; }
+            }
+            if (!done && nacc + nrej > stiff_cap) { status = PFR_ST_STIFF_; done = true; }
+            if (!done && nacc + nrej >= a.max_steps) { status = PFR_ST_MAXSTEPS_; done = true; }
+        }
+        if (done) {
+            if (kc < 0) kc = 0;
+            real yf[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                yf[k] = m_min(m_max(y[k], p.lb), p.ub);
+                y_out[(size_t)k * n + i] = yf[k];
+            }
+            a.status[i] = status;
+            if (a.stats) {
+                a.stats[i] = nacc;
+                a.stats[n + i] = nrej;
+                a.stats[2 * n + i] = nrhs;
+            }
+            if (dense && kc < NTOT - 1) {
+                for (int kk = kc + 1; kk < NTOT; kk++)
+#pragma unroll
+                    for (int k = 0; k < NS; k++) y_dense[((size_t)kk * NS + k) * n + i] = raw ? y[k] : yf[k];
+            }
+            have = false;
+        }
+    }
+}
+
+}  // namespace pfr

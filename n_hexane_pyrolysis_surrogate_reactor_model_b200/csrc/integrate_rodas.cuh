@@ -41,6 +41,7 @@ struct RodasArgs {
     int max_steps;
     const FastTables* tables;  // device copy of the log / exp tables (fastmath.cuh)
     int flags;                 // bit 0: y_dense holds the raw (unclamped) knot states
+    int* work_counter = nullptr;  // bs23_kernel: zero-initialised device counter of its lane-level work queue
 };
 
 namespace rodas4 {

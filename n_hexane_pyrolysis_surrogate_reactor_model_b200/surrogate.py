@@ -30,7 +30,7 @@ INFERENCE_CLAMPS = (1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # ...Eon_singl
 TRAINING_WIDE_CLAMPS = (1.0e-6, 6.0e1, -1.0e1, 1.0e1, -1.0e5, 1.0e5)  # WIDE_Eoff_surrogate_model_training.py:39-53
 TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eoff_surrogate_model_training.py:40-43,54
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
-           "ros3": _lib.METHOD_ROS3}
+           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23}
 
 
 def _ptr(t):
@@ -108,6 +108,7 @@ class SolveResult:
     idx_cut: torch.Tensor | None = None  # [n] (Eon)
     tgrid: torch.Tensor | None = None    # [801, n]
     Tprof: torch.Tensor | None = None    # [801, n]
+    stiff_fallbacks: int = 0             # conditions the explicit fast path handed to the Rosenbrock kernel
 
     def raise_on_failure(self):
         bad = (self.status != 0).nonzero().flatten()
@@ -210,7 +211,10 @@ class Surrogate:
 
     # ------------------------------------------------------------------ a8, a9
     def integrate(self, T0, c0, tgrid=None, Tprof=None, t_end=None, idx_end=None, perm=None, method="rodas4",
-                  precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0, dense_raw=False) -> SolveResult:
+                  precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0, dense_raw=False, stiff_fallback="ros3") -> SolveResult:
+        """pfr_integrate on device arrays.  method: "rodas4" (6-stage Rosenbrock), "ros3" (3-stage Rosenbrock), "bs23" (explicit
+        knot-limited fast path; conditions it flags as stiff are re-integrated with `stiff_fallback`, None to leave them
+        flagged), "rodas4_tpc" (cross-check mapping), "dopri5" (reference-behaviour mode)."""
         T0, c0 = _f32(T0, self.device), _f32(c0, self.device)
         n = T0.numel()
         dt = torch.float64 if precision == 64 else torch.float32
@@ -221,7 +225,30 @@ class Surrogate:
         _lib.check(_lib.lib().pfr_integrate(self.crnn.handle, METHODS[method], precision, n, _ptr(T0), _ptr(c0), _ptr(tgrid),
                                             _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
-        return SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
+        res = SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
+        if method == "bs23" and stiff_fallback:
+            self._integrate_stiff_remainder(res, T0, c0, stiff_fallback, precision, rtol, atol, max_steps, dense_raw)
+        return res
+
+    def _integrate_stiff_remainder(self, res, T0, c0, method, precision, rtol, atol, max_steps, dense_raw):
+        """The explicit fast path (PFR_METHOD_BS23) stops a condition whose knot intervals turn out stiff with
+        PFR_ST_STIFF; those conditions (none for the shipped parameter sets) are integrated again, from the inlet, with
+        the Rosenbrock kernel and their results written over the flagged entries."""
+        stiff = res.status == _lib.ST_STIFF
+        if not bool(stiff.any()):
+            return
+        sel = stiff.nonzero().flatten()
+        sub = self.integrate(T0[sel], c0[sel], tgrid=res.tgrid[:, sel].contiguous(),
+                             Tprof=None if res.Tprof is None else res.Tprof[:, sel].contiguous(),
+                             idx_end=None if res.idx_cut is None else res.idx_cut[sel].contiguous(), method=method,
+                             precision=precision, rtol=rtol, atol=atol, dense=res.dense is not None, max_steps=max_steps,
+                             dense_raw=dense_raw)
+        res.y[:, sel] = sub.y
+        res.status[sel] = sub.status
+        res.stats[:, sel] += sub.stats
+        if res.dense is not None:
+            res.dense[:, :, sel] = sub.dense
+        res.stiff_fallbacks = int(sel.numel())
 
     # ------------------------------------------------------------------ the sweep (hot path)
     def sweep(self, T, P, L=None, u0=None, method="rodas4", precision=64, rtol=1e-6, atol=1e-6, sort=True,
@@ -247,13 +274,13 @@ class Surrogate:
             return res
         n = T.numel()
         t_full, _ = self.time_grid(T, P, None, None, want_grid=True, out=None if keep_grids else self._scratch("t_full", n))
-        Tprof = self.temp_profile(T, P, out=None if keep_grids else self._scratch("Tprof", n))
         if L is None:
             idx = torch.full((T.numel(),), NTOTAL - 1, dtype=torch.int32, device=self.device)
             tend = t_full[NTOTAL - 1].clone()
         else:
             _, tend = self.time_grid(T, P, L, u0, want_grid=False, want_end=True)
             idx = self.idx_cut(t_full, tend)
+        Tprof = self.temp_profile(T, P, out=None if keep_grids else self._scratch("Tprof", n))
         perm = torch.argsort(idx, descending=True).to(torch.int32) if sort else None
         res = self.integrate(T, c0, tgrid=t_full, Tprof=Tprof, idx_end=idx, perm=perm, method=method, precision=precision,
                              rtol=rtol, atol=atol)

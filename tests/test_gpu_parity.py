@@ -262,6 +262,78 @@ def test_ros3_eon_shipped_conditions_envelope(surrogates, conditions):
     assert float(a.stats[2].double().mean()) < 0.45 * float(b.stats[2].double().mean())   # a third of the right-hand sides
 
 
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_bs23_fast_path_vs_converged_truth_golden(surrogates, golden, variant):
+    """The explicit knot-limited fast path (PFR_METHOD_BS23) converges to the same solution as the Rosenbrock kernels:
+    within 1e-6 of the converged oracle solution at rtol = atol = 1e-10 (outlet and every 50th knot of the dense output),
+    counters obey rhs = 3 x (attempts + 1) (a condition enters with one zero-length step that produces f(t0, y0)), and at the tolerance the bench runs it with (1e-8) it is closer to the converged
+    solution than RODAS4 at the reference's 1e-6."""
+    s = surrogates("LLNL", variant)
+    tg, Tp, idx = _grids(golden, variant)
+    tgd = torch.as_tensor(tg.T.copy()).cuda()
+    Tpd = torch.as_tensor(Tp.T.copy()).cuda() if variant == "Eon" else None
+    idxd = torch.as_tensor(idx).cuda() if variant == "Eon" else None
+    kw = dict(tgrid=tgd, Tprof=Tpd, idx_end=idxd)
+    truth = np.clip(golden[f"{variant}/truth_outlet"], 1e-6, 60.0)
+    tight = s.integrate(golden["T"], golden["c0"][:, 6], method="bs23", rtol=1e-10, atol=1e-10, dense=True, stiff_fallback=None, **kw)
+    assert int(tight.status.abs().sum()) == 0
+    st = tight.stats.cpu().numpy()
+    assert np.array_equal(st[2], 3 * (st[0] + st[1] + 1))
+    e_tight = np.max(rel_err(tight.y.cpu().numpy().T, truth))
+    assert e_tight < 1e-6, e_tight
+    dense = tight.dense.cpu().numpy()
+    for j, k in enumerate(range(0, 801, 50)):
+        ok = k <= idx
+        if ok.any():
+            ref = np.clip(golden[f"{variant}/truth_knots_every50"][ok, j, :], 1e-6, 60.0)
+            assert np.max(rel_err(dense[k][:, ok].T, ref)) < 1e-6
+    bench = s.integrate(golden["T"], golden["c0"][:, 6], method="bs23", rtol=1e-8, atol=1e-8, **kw)
+    rodas = s.integrate(golden["T"], golden["c0"][:, 6], method="rodas4", rtol=1e-6, atol=1e-6, **kw)
+    e_bench = rel_err(bench.y.cpu().numpy().T, truth).max()
+    e_rodas = rel_err(rodas.y.cpu().numpy().T, truth).max()
+    print(f"bs23 {variant}: tight {e_tight:.2e}, 1e-8 {e_bench:.2e}, rodas4 1e-6 {e_rodas:.2e}, attempts at 1e-10 {(st[0] + st[1]).mean():.0f}")
+    assert e_bench < 1e-5 and e_bench <= e_rodas
+
+
+def test_bs23_eon_shipped_conditions_envelope(surrogates, conditions):
+    """All 400 shipped 4-D conditions on the GPU's own grids, every mechanism: the fast path at 1e-8 against RODAS4 at 1e-11;
+    its median error must beat RODAS4 at the reference's 1e-6 (measured 4-14x smaller), its worst case stay below 5e-5
+    (measured 0.9e-5 .. 2.4e-5; RODAS4 at 1e-6: 0.8e-5 .. 2.5e-5 -- the worst cases of both are single conditions whose
+    first steps straddle the kink of the state clamp at 1e-6 mol/m3), with fewer right-hand sides, and none of the trained
+    parameter sets may trip the stiffness guard."""
+    T, P, L, U = cond4(conditions)
+    for mech in ("LLNL", "JetSurf", "NUIG"):
+        s = surrogates(mech, "Eon")
+        ref = s.sweep(T, P, L, U, method="rodas4", rtol=1e-11, atol=1e-11).raise_on_failure().y.cpu().numpy().T
+        a = s.sweep(T, P, L, U, method="bs23", rtol=1e-8, atol=1e-8).raise_on_failure()
+        b = s.sweep(T, P, L, U, method="rodas4", rtol=1e-6, atol=1e-6).raise_on_failure()
+        ea, eb = rel_err(a.y.cpu().numpy().T, ref).max(1), rel_err(b.y.cpu().numpy().T, ref).max(1)
+        print(f"{mech}: bs23@1e-8 max {ea.max():.2e} median {np.median(ea):.2e}; rodas4@1e-6 max {eb.max():.2e} median {np.median(eb):.2e}")
+        assert a.stiff_fallbacks == 0
+        assert ea.max() < 5e-5 and np.median(ea) <= 0.5 * np.median(eb)
+        assert float(a.stats[2].double().mean()) < 0.65 * float(b.stats[2].double().mean())
+
+
+def test_bs23_stiff_guard_hands_over_to_rosenbrock(surrogates, golden):
+    """Stretch the golden time grid 2000x at constant temperature: the knot intervals become long against the fastest
+    chemical time scale, the explicit method is stability-limited, and the guard must stop those conditions with
+    PFR_ST_STIFF.  With the fallback enabled (the default) the same call returns the Rosenbrock result for them."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    s = surrogates("LLNL", "Eoff")
+    tgd = torch.as_tensor((golden["Eoff/tgrid"] * 2000.0).T.copy()).cuda()
+    T0 = np.full(16, 1150.0, np.float32)
+    kw = dict(tgrid=tgd, rtol=1e-6, atol=1e-6)
+    bare = s.integrate(T0, golden["c0"][:, 6], method="bs23", stiff_fallback=None, **kw)
+    flagged = bare.status == _lib.ST_STIFF
+    assert int(flagged.sum()) > 0 and int(((bare.status != 0) & ~flagged).sum()) == 0
+    auto = s.integrate(T0, golden["c0"][:, 6], method="bs23", **kw)
+    ros = s.integrate(T0, golden["c0"][:, 6], method="ros3", **kw)
+    assert int(auto.status.abs().sum()) == 0 and auto.stiff_fallbacks == int(flagged.sum())
+    assert torch.equal(auto.y[:, flagged], ros.y[:, flagged])
+    tight = s.integrate(T0, golden["c0"][:, 6], method="rodas4", tgrid=tgd, rtol=1e-10, atol=1e-10)
+    assert np.max(rel_err(auto.y.cpu().numpy().T, tight.y.cpu().numpy().T)) < 1e-3
+
+
 def test_rodas_fp32_state(surrogates, golden):
     s = surrogates("LLNL", "Eoff")
     tg, _, _ = _grids(golden, "Eoff")
@@ -436,7 +508,7 @@ def test_sweep_sorted_equals_unsorted(surrogates, conditions):
     assert torch.equal(a.y, b.y)                                # the permutation only reorders threads
 
 
-@pytest.mark.parametrize("method,precision", [("rodas4", 64), ("rodas4", 32), ("rodas4_tpc", 64), ("dopri5", 32), ("ros3", 64)])
+@pytest.mark.parametrize("method,precision", [("rodas4", 64), ("rodas4", 32), ("rodas4_tpc", 64), ("dopri5", 32), ("ros3", 64), ("bs23", 64), ("bs23", 32)])
 def test_integrators_ragged_batch_sizes(surrogates, conditions, method, precision):
     """Batches that do not fill a warp / a 10-condition group / a CTA: every condition is an independent problem, so
     the first n columns of a full-batch run and an n-condition run are bit-identical (Eon grids, outlet at idx_cut)."""

@@ -52,7 +52,7 @@ def main():
         ref = run("rodas4", 1e-11).y.clone()
         scale = torch.clamp(ref.abs(), min=1e-3)
         for meth in methods:
-            for tol in (1e-5, 1e-6, 1e-7, 1e-8, 1e-9):
+            for tol in (1e-5, 1e-6, 1e-7, 3e-8, 1e-8, 1e-9):
                 ms, res = timed(lambda: run(meth, tol))
                 e = ((res.y - ref).abs() / scale).amax(0)
                 st = res.stats.double()
