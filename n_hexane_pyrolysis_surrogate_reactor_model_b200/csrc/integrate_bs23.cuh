@@ -261,21 +261,33 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             const double hs = fresh ? 0.0 : (clip ? dist : hprop);
             const real h = real(hs);
             const real tau = real(t - tk);   // time since the knot: T(t + c h) = Tk + slope (tau + c h)
-            real k2[NS], k3[NS], w[NS];
+            // The three stages run as a rolled loop so that the right-hand side exists once in the instruction stream (three
+            // inlined copies made the loop body ~59 KB and instruction fetch the largest stall, 22 % of all stall cycles).
+            // The stage index is warp-uniform.  acc / er accumulate the solution and error combinations as the slopes arrive:
+            //   y1 = y + h (2/9 k1 + 1/3 k2 + 4/9 k3),   err = h (-5/72 k1 + 1/12 k2 + 1/9 k3 - 1/8 k4)
+            real k2[NS], w[NS], acc[NS], er[NS];
 #pragma unroll
             for (int k = 0; k < NS; k++) w[k] = fma(real(0.5) * h, k1[k], y[k]);
-            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? fma(slope, fma(real(0.5), h, tau), Tk) : Tk, w, k2);
+#pragma unroll 1
+            for (int stage = 0; stage < 3; stage++) {
+                const real cs = stage == 0 ? real(0.5) : (stage == 1 ? real(0.75) : real(1));
+                const real Ts = kRamp ? ((stage == 2 && clip) ? Tk1 : fma(slope, fma(cs, h, tau), Tk)) : Tk;
+                rhs_tpc<real>(p, sc, zthr, dthr, Ts, w, k2);
+                if (stage == 0) {
 #pragma unroll
-            for (int k = 0; k < NS; k++) w[k] = fma(real(0.75) * h, k2[k], y[k]);
-            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? fma(slope, fma(real(0.75), h, tau), Tk) : Tk, w, k3);
-            // third-order solution; k2, k3 fold into the error combination and die here
-            real er[NS];
+                    for (int k = 0; k < NS; k++) {
+                        acc[k] = fma(real(1.0 / 3.0), k2[k], real(2.0 / 9.0) * k1[k]);
+                        er[k] = fma(real(1.0 / 12.0), k2[k], real(-5.0 / 72.0) * k1[k]);
+                        w[k] = fma(real(0.75) * h, k2[k], y[k]);
+                    }
+                } else if (stage == 1) {
 #pragma unroll
-            for (int k = 0; k < NS; k++) {
-                w[k] = fma(h, fma(real(4.0 / 9.0), k3[k], fma(real(1.0 / 3.0), k2[k], real(2.0 / 9.0) * k1[k])), y[k]);
-                er[k] = fma(real(1.0 / 9.0), k3[k], fma(real(1.0 / 12.0), k2[k], real(-5.0 / 72.0) * k1[k]));
-            }
-            rhs_tpc<real>(p, sc, zthr, dthr, kRamp ? (clip ? Tk1 : fma(slope, tau + h, Tk)) : Tk, w, k2);   // k4 = f(t + h, y1): next k1
+                    for (int k = 0; k < NS; k++) {
+                        w[k] = fma(h, fma(real(4.0 / 9.0), k2[k], acc[k]), y[k]);   // third-order solution y1
+                        er[k] = fma(real(1.0 / 9.0), k2[k], er[k]);
+                    }
+                }
+            }   // k2 now holds k4 = f(t + h, y1): the next step's k1
             nrhs += 3;
             real e2 = real(0), d0 = real(0), d1 = real(0);
             bool finite = true;

@@ -136,15 +136,23 @@ class Surrogate:
         self.crnn = CrnnModel(models.crnn, clamps)
         self.time_mlp = MlpModel(models.time_mlp, mlp_mode)
         self.temp_mlp = MlpModel(models.temp_mlp, mlp_mode) if models.temp_mlp is not None else None
-        self._ws = None
+        self._ws = {}
         self._grids = {}
+        self._side = None
 
     # ------------------------------------------------------------------ plumbing
-    def _workspace(self, n: int):
+    def _workspace(self, n: int, slot: int = 0):
+        """MLP activation workspace; `slot` > 0: a separate one for an MLP pass that runs concurrently on a side stream."""
         need = _lib.lib().pfr_mlp_workspace_bytes(n, self.chunk)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < need:
+            self._ws[slot] = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _side_streams(self):
+        if self._side is None:
+            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._side
 
     # ------------------------------------------------------------------ a1
     def inlet_concentration(self, T, P) -> torch.Tensor:
@@ -169,25 +177,25 @@ class Surrogate:
             self._grids[name] = buf = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
         return buf
 
-    def time_grid(self, T, P, L=None, u0=None, want_grid=True, want_end=False, raw=False, out=None):
+    def time_grid(self, T, P, L=None, u0=None, want_grid=True, want_end=False, raw=False, out=None, end_out=None, ws_slot=0):
         """(tgrid[801,n] | None, t_end[n] | None).  L/u0 None -> the full-length grid at (1.0 m, 2.5 m/s)."""
         T, P = _f32(T, self.device), _f32(P, self.device)
         L = None if L is None else _f32(L, self.device)
         u0 = None if u0 is None else _f32(u0, self.device)
         n = T.numel()
-        ws = self._workspace(n)
+        ws = self._workspace(n, ws_slot)
         grid = (out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)) if want_grid else None
-        tend = torch.empty(n, dtype=torch.float32, device=self.device) if want_end else None
+        tend = (end_out if end_out is not None else torch.empty(n, dtype=torch.float32, device=self.device)) if want_end else None
         _lib.check(_lib.lib().pfr_time_grid(self.time_mlp.handle, _ptr(T), _ptr(P), _ptr(L), _ptr(u0), n, _ptr(grid), _ptr(tend),
                                             int(raw), _ptr(ws), ws.numel(), self.chunk, _stream()), "pfr_time_grid")
         return grid, tend
 
-    def temp_profile(self, T, P, raw=False, out=None) -> torch.Tensor:
+    def temp_profile(self, T, P, raw=False, out=None, ws_slot=0) -> torch.Tensor:
         if self.temp_mlp is None:
             raise _lib.PfrError("this model set has no temperature MLP (Eoff variant)")
         T, P = _f32(T, self.device), _f32(P, self.device)
         n = T.numel()
-        ws = self._workspace(n)
+        ws = self._workspace(n, ws_slot)
         prof = out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib().pfr_temp_profile(self.temp_mlp.handle, _ptr(T), _ptr(P), n, _ptr(prof), int(raw), _ptr(ws),
                                                ws.numel(), self.chunk, _stream()), "pfr_temp_profile")
@@ -252,13 +260,25 @@ class Surrogate:
 
     # ------------------------------------------------------------------ the sweep (hot path)
     def sweep(self, T, P, L=None, u0=None, method="rodas4", precision=64, rtol=1e-6, atol=1e-6, sort=True,
-              keep_grids=False) -> SolveResult:
+              keep_grids=False, integrator_events: list | None = None) -> SolveResult:
         """Outlet species for a batch of conditions.
 
         Eoff (...Eoff_single_model.py:339-369): time MLP at (T,P,L,u0) -> enforce_strict -> integrate at T = T0
         to the last knot.  Eon (...Eon_single_model.py:296-354): temperature MLP + full-length time MLP at
         (T,P,1.0,2.5) -> integrate; the outlet is the state at knot idx_cut = argmin|t_full - t_short[-1]|.
+        integrator_events: a list that receives one (start, end) pair of CUDA events recorded around the integrator launch
+        (bench.py times the dominant kernel inside the timed steps with it).
         """
+        def timed_integrate(*a, **k):
+            if integrator_events is None:
+                return self.integrate(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = self.integrate(*a, **k)
+            e1.record()
+            integrator_events.append((e0, e1))
+            return r
+
         T, P = _f32(T, self.device), _f32(P, self.device)
         L = None if L is None else _f32(L, self.device)
         u0 = None if u0 is None else _f32(u0, self.device)
@@ -269,21 +289,38 @@ class Surrogate:
             else:
                 tgrid, tend = self.time_grid(T, P, L, u0, want_grid=False, want_end=True)
             perm = torch.argsort(T, descending=True).to(torch.int32) if sort else None
-            res = self.integrate(T, c0, t_end=tend, perm=perm, method=method, precision=precision, rtol=rtol, atol=atol)
+            res = timed_integrate(T, c0, t_end=tend, perm=perm, method=method, precision=precision, rtol=rtol, atol=atol)
             res.tgrid = tgrid
             return res
         n = T.numel()
+        # The three MLP passes are independent.  Their GEMM kernels fill the SMs one at a time (one persistent CTA per SM with
+        # ~210 KB of shared memory), but the HBM-bound kernels in between (first layer, enforce_strict, idx_cut) of one pass
+        # fit beside the GEMM CTAs of another: two side streams let them overlap.  Outputs are allocated on the calling
+        # stream, which waits for both side streams before it goes on.
+        main = torch.cuda.current_stream()
+        s1, s2 = self._side_streams()
+        Tprof = torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device) if keep_grids else self._scratch("Tprof", n)
+        tend = None if L is None else torch.empty(n, dtype=torch.float32, device=self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(s1):
+            s1.wait_event(ready)
+            self.temp_profile(T, P, out=Tprof, ws_slot=1)
+        if L is not None:
+            with torch.cuda.stream(s2):
+                s2.wait_event(ready)
+                self.time_grid(T, P, L, u0, want_grid=False, want_end=True, end_out=tend, ws_slot=2)
         t_full, _ = self.time_grid(T, P, None, None, want_grid=True, out=None if keep_grids else self._scratch("t_full", n))
+        main.wait_stream(s1)
+        main.wait_stream(s2)
         if L is None:
             idx = torch.full((T.numel(),), NTOTAL - 1, dtype=torch.int32, device=self.device)
             tend = t_full[NTOTAL - 1].clone()
         else:
-            _, tend = self.time_grid(T, P, L, u0, want_grid=False, want_end=True)
             idx = self.idx_cut(t_full, tend)
-        Tprof = self.temp_profile(T, P, out=None if keep_grids else self._scratch("Tprof", n))
         perm = torch.argsort(idx, descending=True).to(torch.int32) if sort else None
-        res = self.integrate(T, c0, tgrid=t_full, Tprof=Tprof, idx_end=idx, perm=perm, method=method, precision=precision,
-                             rtol=rtol, atol=atol)
+        res = timed_integrate(T, c0, tgrid=t_full, Tprof=Tprof, idx_end=idx, perm=perm, method=method, precision=precision,
+                              rtol=rtol, atol=atol)
         res.t_end = tend
         if not keep_grids:
             res.tgrid = res.Tprof = None
