@@ -45,52 +45,66 @@ STEP_INSTR = {"rodas4": FP64_STEP, "ros3": FP64_STEP_ROS3, "bs23": FP64_STEP_BS2
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled every 100 ms while the timed region runs.  In-process NVML
+    (nvidia_ml_py) on a thread, initialised before the first step: an `nvidia-smi -lms` child process was measured to stall
+    kernel launches for ~130 ms once, early in its life, which showed up as one slow step in the timed region."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.h, self.stop = index, [], None, threading.Event()
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-            # nvidia-smi's start-up (NVML initialisation) holds driver locks for ~100 ms and showed up as one slow step early in
-            # the timed region: wait for its first sample before any step is launched
-            t0 = time.time()
-            while not self.rows and time.time() - t0 < 5.0:
-                time.sleep(0.02)
         except Exception:
-            self.proc = None
+            self.h = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.rows.append((sm, reasons))
+
+    def _run(self):
+        while not self.stop.wait(0.1):
+            try:
+                self._sample()
+            except Exception:
+                break
 
     def __exit__(self, *exc):
-        if self.proc:
-            self.proc.terminate()
+        self.stop.set()
+        if self.h is not None:
             self.th.join(timeout=2)
         return False
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[0] for r in self.rows[1:]] or [r[0] for r in self.rows]
+        reasons = set()
+        for _, bits in self.rows[1:]:
+            for b, nme in self.BITS.items():
+                if bits & b:
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "mx", None), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "NVML (nvidia_ml_py), in-process, every 100 ms during the timed steps"}
 
 
 def _flops(stats, energy_on, method="rodas4"):
@@ -135,8 +149,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def time_steps(fn, steps, warmup):
+        out = None
         for _ in range(warmup):
-            fn()
+            out = fn()   # same lifetime pattern as the timed loop: the previous result is still alive while the next one is
+                         # allocated, so the caching allocator reaches its steady state (two result sets) during warm-up
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.lib().pfr_launch_count()

@@ -32,11 +32,11 @@
 namespace pfr {
 
 constexpr int BS23_BLOCK = 128;
-constexpr int BS23_CTAS_PER_SM = 2;   // persistent grid: 255 registers x 128 threads, two CTAs fill the register file
-constexpr int PFR_ST_STIFF_ = 4;
 #ifndef PFR_BS23_MINB
-#define PFR_BS23_MINB 2   // 255 registers, 8 warps / SM: measured 11 % faster than 168 registers with spills
+#define PFR_BS23_MINB 2   // CTAs per SM.  2: 250 registers, no spills, 8 warps / SM; 3 (168 registers, 94 B of spills): 30 % slower
 #endif
+constexpr int BS23_CTAS_PER_SM = PFR_BS23_MINB;   // persistent grid: 250 registers x 128 threads, two CTAs fill the register file
+constexpr int PFR_ST_STIFF_ = 4;
 
 template <typename real> __device__ __forceinline__ real t_log(real x, const FastTables& ft);
 template <> __device__ __forceinline__ double t_log<double>(double x, const FastTables& ft) { return fast_log(x, ft.logtab); }
