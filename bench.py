@@ -115,7 +115,7 @@ def _flops(stats, energy_on, method="rodas4"):
     return 2.0 * instr, {"accepted_mean": acc / stats.shape[1], "rejected_mean": rej / stats.shape[1], "rhs_mean": rhs / stats.shape[1]}
 
 
-def run_ours(args):
+def run_ours(args, emit=print):
     import torch
     import torch.distributed as dist
 
@@ -300,7 +300,7 @@ def run_ours(args):
                      "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
                      "kernel_ms": result["kms"], "kernel_ms_source": "CUDA events around the kernel launch inside the timed steps (mean over the steps)",
                      "kernel_share_of_step": e["integrator_share_of_step"],
-                     "traffic": 51.8e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01g_ncu_full_bs23_fp64.txt: 51.8 KB per condition x n "
+                     "traffic": 76.5e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01g_ncu_full_bs23_fp64.txt: 76.5 KB per condition x n "
                                                                 "(the two [801][n] float32 grids are gathered through the cost-sort permutation: one 32-byte sector per 4-byte knot value)",
                      "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
                                    f"BS23 step overhead {FP64_STEP_BS23} (stage sums, error norm; ROS3: {FP64_STEP_ROS3}, RODAS4: {FP64_STEP}); see DESIGN.md"},
@@ -310,7 +310,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +380,7 @@ def cpu_baseline(args, variant="Eon", sample=None):
     return out
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -400,7 +400,7 @@ def run_reference(args):
                        "note": "the reference scripts cannot run (torchdiffeq, cantera and the label files are absent): oracle port timed"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def main():
@@ -417,10 +417,20 @@ def main():
     ap.add_argument("--bs23-tol", type=float, default=1e-8, help="rtol = atol of the explicit fast path on the Eon path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: whatever libraries print while the run is going on (NCCL's version banner, ...)
+    # is sent to stderr by pointing file descriptor 1 there until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    try:
+        (run_reference if args.impl == "reference" else run_ours)(args, lines.append)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":
