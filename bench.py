@@ -269,6 +269,7 @@ def run_ours(args, emit=print):
         del sur, r, res
         torch.cuda.empty_cache()
     variants["train_step_WIDE_Eoff"] = training_variant(dev, world, rank, time_steps)
+    variants["mlp_train_step_2D"] = mlp_training_variant(dev, time_steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,6 +342,44 @@ def training_variant(dev, world, rank, time_steps):
             "reference": "WIDE_Eoff_surrogate_model_training.py: ~0.225 s per sample per CPU core (SURVEY 6), batch size 1"}
 
 
+def _mlp_training_problem():
+    """Temperature-MLP training data of temp_profile_model_training_2D.py's shape: the 800 (T, P) rows of sampling_case_2D.csv with
+    labels from the shipped LLNL temperature MLP (teacher; the Cantera label files are absent), evaluated by the device
+    trainer's own forward kernels."""
+    import torch
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.mlp_training import INPUT_SCALE, MlpDataset, MlpTrainer, TEMP_2D_SETTINGS
+    a = np.load(os.path.join(ROOT, "tests", "golden", "conditions.npz"))["training_2D"]
+    teacher = ModelSet.from_packed(os.path.join(GOLD, "LLNL.npz"), "Eon").temp_mlp
+    sc = INPUT_SCALE[2]
+    x = ((a - sc[0]) / (sc[1] - sc[0])).astype(np.float32)
+    y = MlpTrainer(teacher.w, teacher.b, TEMP_2D_SETTINGS).forward(torch.from_numpy(x)).double().cpu().numpy()
+    return MlpDataset(a, y * (teacher.out_max - teacher.out_min) + teacher.out_min)
+
+
+def mlp_training_variant(dev, time_steps):
+    """optimisation steps of the temperature-predictor MLP (batch 32, Adam) on the device."""
+    import torch
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.mlp_training import MlpTrainer, TEMP_2D_SETTINGS, initial_parameters
+    ds = _mlp_training_problem()
+    xt, yt = (torch.from_numpy(v).to(dev) for v in ds.parts["training"])
+    w0, b0 = initial_parameters(2, seed=0)
+    tr = MlpTrainer(w0, b0, TEMP_2D_SETTINGS, dev)
+    loss = torch.zeros((), device=dev)
+    batches = [(xt[i:i + 32].contiguous(), yt[i:i + 32].contiguous()) for i in range(0, 640, 32)]
+    first = []
+
+    def epoch():
+        for bx, by in batches:
+            tr.step(bx, by, 1e-3, loss)
+        first.append(float(loss)) if len(first) < 1 else None
+        return loss
+    ms, _, launches = time_steps(epoch, 5, 3)
+    return {"value": 5 * len(batches) / (ms * 1e-3), "unit": "optimisation steps/s (batch 32)", "ms_per_step": ms / (5 * len(batches)),
+            "kernel_launches_per_step": launches / (5 * len(batches)), "loss_after_first_epoch": first[0], "loss_last": float(loss),
+            "reference": "temp_profile_model_training_2D.py:145-160 (torch, batch 32, Adam 1e-3); torch CPU timing under cpu_baseline"}
+
+
 def cpu_baseline(args, variant="Eon", sample=None):
     """The oracle's restatement of the reference drivers (torch CPU ops, per-condition Python loop) on all host cores."""
     from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
@@ -375,6 +414,20 @@ def cpu_baseline(args, variant="Eon", sample=None):
     t0 = time.time()
     CO.dopri5_batch(tg, Tp, R.inlet_concentration(T[sel], P[sel]), ms.crnn.w_in, ms.crnn.w_b, ms.crnn.w_out, report=rep, nthreads=cores)
     t_ode = time.time() - t0
+    try:   # the reference's own torch operators, one epoch of the temperature-MLP training loop on the CPU
+        import torch
+        from n_hexane_pyrolysis_surrogate_reactor_model_b200.mlp_training import initial_parameters
+        from oracle import mlp_training_reference as O
+        rng = np.random.default_rng(0)
+        w0, b0 = initial_parameters(2, seed=0)
+        bt = [(rng.random((32, 2), dtype=np.float32), rng.random((32, 800), dtype=np.float32)) for _ in range(20)]
+        O.run_steps(w0, b0, bt[:2], [1e-3] * 2)
+        t0 = time.time()
+        O.run_steps(w0, b0, bt, [1e-3] * 20)
+        out["mlp_training_torch_cpu"] = {"steps_per_s": 20 / (time.time() - t0), "threads": torch.get_num_threads(), "batch": 32,
+                                         "what": "oracle/mlp_training_reference.py: nn.Linear / MSELoss / Adam of temp_profile_model_training_2D.py"}
+    except Exception as exc:   # noqa: BLE001
+        out["mlp_training_torch_cpu"] = {"unavailable": repr(exc)}
     out["c_port_for_context"] = {"ode_trajectories_per_s": m / t_ode, "batched_torch_mlp_trajectories_per_s": m / t_mlp, "sample": m,
                                  "note": "compiled C dopri5 (float32, 801 outputs) on all cores + batched torch-CPU MLPs; not what the reference runs"}
     return out

@@ -49,6 +49,7 @@ extern "C" {
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;
+typedef struct pfr_mlp_trainer* pfr_mlp_trainer_t;
 
 int pfr_version(void);
 const char* pfr_status_string(int code);
@@ -137,6 +138,25 @@ int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream)
  * FCD, Max_Norm. */
 int pfr_accuracy(const void* dense, int precision, const float* label, const int* idx_end, int n, int abs_den, double* out,
                  void* stream);
+
+/* ---- predictor-MLP training ----------------------------------------------------------------------
+ * One optimisation step of  TEMP_PRED_MODEL_TRAINING/temp_profile_model_training_2D.py:145-160  /
+ * TIME_PRED_MODEL_TRAINING/time_profile_model_training_4D.py:174-190 :
+ *   outputs = model(images); loss = nn.MSELoss()(outputs, labels); optimizer.zero_grad(); loss.backward(); optimizer.step()
+ * with torch.optim.Adam(betas, eps; no weight decay) on the 2|4 -> 512 -> 512 -> 512 -> 800 ReLU network (nn.Linear layout:
+ * weights[l] is [out][in] row-major, biases[l] [out], host pointers at creation).  The trainer owns parameters, Adam moments
+ * and activations on the device. */
+int pfr_mlp_trainer_create(int in_dim, const float* const weights[4], const float* const biases[4], pfr_mlp_trainer_t* out);
+int pfr_mlp_trainer_destroy(pfr_mlp_trainer_t t);
+/* x [B][in_dim], y [B][800] (already scaled as the Dataset classes do), B <= 32 (the scripts' batch size), device pointers;
+ * loss: one float on the device (MSE before the update).  lr is this step's learning rate (StepLR lives on the host). */
+int pfr_mlp_trainer_step(pfr_mlp_trainer_t t, const float* x, const float* y, int B, double lr, double beta1, double beta2,
+                         double eps, float* loss, void* stream);
+/* model.eval() forward: x [n][in_dim] -> out [n][800]; and the MSE of one batch without an update (validation loop) */
+int pfr_mlp_trainer_forward(pfr_mlp_trainer_t t, const float* x, int n, float* out, void* stream);
+int pfr_mlp_trainer_loss(pfr_mlp_trainer_t t, const float* x, const float* y, int B, float* loss, void* stream);
+/* model.state_dict(): copies the current parameters to host arrays of the creation shapes (synchronises the device) */
+int pfr_mlp_trainer_read(pfr_mlp_trainer_t t, float* const weights[4], float* const biases[4]);
 
 /* Parity hook for the table-driven double-precision log (kind 0, x positive normal) / exp (kind 1, |x| < 700)
  * used inside the Rosenbrock kernel in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).

@@ -61,6 +61,16 @@ def _declare(lib):
     lib.pfr_reduce_rows.restype = c_int
     lib.pfr_accuracy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.pfr_accuracy.restype = c_int
+    fpp = ctypes.POINTER(c_float_p)
+    lib.pfr_mlp_trainer_create.argtypes = [c_int, fpp, fpp, ctypes.POINTER(c_void_p)]
+    lib.pfr_mlp_trainer_destroy.argtypes = [c_void_p]
+    lib.pfr_mlp_trainer_step.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p, c_void_p]
+    lib.pfr_mlp_trainer_forward.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.pfr_mlp_trainer_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.pfr_mlp_trainer_read.argtypes = [c_void_p, fpp, fpp]
+    for name in ("pfr_mlp_trainer_create", "pfr_mlp_trainer_destroy", "pfr_mlp_trainer_step", "pfr_mlp_trainer_forward",
+                 "pfr_mlp_trainer_loss", "pfr_mlp_trainer_read"):
+        getattr(lib, name).restype = c_int
     lib.pfr_measure_peaks.argtypes = [c_double_p]
     lib.pfr_fastmath.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.pfr_fastmath.restype = c_int

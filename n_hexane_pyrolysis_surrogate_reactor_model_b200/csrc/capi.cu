@@ -18,6 +18,7 @@
 #include "adjoint.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_train.cuh"
 
 using namespace pfr;
 
@@ -598,6 +599,124 @@ extern "C" int pfr_reduce_rows(const double* x, int rows, int n, double* out, vo
     if (!x || !out || rows < 0 || n < 0) return PFR_EINVAL;
     reduce_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, n, out);
     CK_LAUNCH("reduce_rows_kernel");
+    return PFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Predictor-MLP training step (mlp_train.cuh)
+struct pfr_mlp_trainer {
+    int in_dim;
+    long long step;
+    float *W[4], *b[4], *mW[4], *vW[4], *mb[4], *vb[4];
+    float *act[4], *actT[4];   // ReLU outputs of fc1..fc3 and the network output, batch-major [32][N] and feature-major [N][32]
+    float *grad[2];            // ping-pong gradient buffers, feature-major [800][32]
+};
+static inline int tr_K(const pfr_mlp_trainer* t, int l) { return l == 0 ? t->in_dim : mt::HID; }
+static inline int tr_N(int l) { return l == 3 ? mt::OUT : mt::HID; }
+
+extern "C" int pfr_mlp_trainer_create(int in_dim, const float* const weights[4], const float* const biases[4], pfr_mlp_trainer_t* out) {
+    if (!out || !weights || !biases || (in_dim != 2 && in_dim != 4)) return PFR_EINVAL;
+    pfr_mlp_trainer* t = new (std::nothrow) pfr_mlp_trainer();
+    if (!t) return PFR_ECUDA;
+    t->in_dim = in_dim;
+    t->step = 0;
+    for (int l = 0; l < 4; l++) {
+        const size_t nw = (size_t)tr_N(l) * tr_K(t, l), nb = (size_t)tr_N(l);
+        CK(cudaMalloc((void**)&t->W[l], nw * 4)); CK(cudaMalloc((void**)&t->mW[l], nw * 4)); CK(cudaMalloc((void**)&t->vW[l], nw * 4));
+        CK(cudaMalloc((void**)&t->b[l], nb * 4)); CK(cudaMalloc((void**)&t->mb[l], nb * 4)); CK(cudaMalloc((void**)&t->vb[l], nb * 4));
+        CK(cudaMemcpy(t->W[l], weights[l], nw * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(t->b[l], biases[l], nb * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(t->mW[l], 0, nw * 4)); CK(cudaMemset(t->vW[l], 0, nw * 4));
+        CK(cudaMemset(t->mb[l], 0, nb * 4)); CK(cudaMemset(t->vb[l], 0, nb * 4));
+        CK(cudaMalloc((void**)&t->act[l], (size_t)mt::MAXB * tr_N(l) * 4));
+        CK(cudaMalloc((void**)&t->actT[l], (size_t)mt::MAXB * tr_N(l) * 4));
+    }
+    for (int g = 0; g < 2; g++) CK(cudaMalloc((void**)&t->grad[g], (size_t)mt::MAXB * mt::OUT * 4));
+    *out = t;
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_trainer_destroy(pfr_mlp_trainer_t t) {
+    if (!t) return PFR_OK;
+    for (int l = 0; l < 4; l++) {
+        cudaFree(t->W[l]); cudaFree(t->mW[l]); cudaFree(t->vW[l]); cudaFree(t->b[l]); cudaFree(t->mb[l]); cudaFree(t->vb[l]);
+        cudaFree(t->act[l]); cudaFree(t->actT[l]);
+    }
+    cudaFree(t->grad[0]); cudaFree(t->grad[1]);
+    delete t;
+    return PFR_OK;
+}
+
+// fc1..fc4 on at most 32 rows; activations stay in the trainer's buffers (both layouts), the network output in act[3]
+static int trainer_forward32(pfr_mlp_trainer_t t, const float* x, int B, cudaStream_t st) {
+    for (int l = 0; l < 4; l++) {
+        const int K = tr_K(t, l), N = tr_N(l);
+        const float* in = l == 0 ? x : t->actT[l - 1];
+        const int sk = l == 0 ? 1 : mt::MAXB, sb = l == 0 ? K : 1;   // x is [B][in_dim]; hidden activations feature-major
+        if (l < 3) mt::linear_fwd_kernel<true><<<(N + 7) / 8, 256, 0, st>>>(in, sk, sb, t->W[l], t->b[l], B, K, N, t->act[l], t->actT[l]);
+        else mt::linear_fwd_kernel<false><<<(N + 7) / 8, 256, 0, st>>>(in, sk, sb, t->W[l], t->b[l], B, K, N, t->act[l], t->actT[l]);
+        CK_LAUNCH("linear_fwd_kernel");
+    }
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_trainer_step(pfr_mlp_trainer_t t, const float* x, const float* y, int B, double lr, double beta1, double beta2,
+                                    double eps, float* loss, void* stream) {
+    if (!t || !x || !y || !loss || B < 1 || B > mt::MAXB || !(lr > 0)) return PFR_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = trainer_forward32(t, x, B, st);
+    if (rc) return rc;
+    mt::mse_kernel<<<1, 1024, 0, st>>>(t->act[3], y, B, mt::OUT, t->grad[0], loss);
+    CK_LAUNCH("mse_kernel");
+    t->step++;
+    const double bc1 = 1.0 - pow(beta1, (double)t->step), bc2 = 1.0 - pow(beta2, (double)t->step);
+    const mt::AdamArgs a{(float)beta1, (float)beta2, (float)eps, (float)(lr / bc1), (float)sqrt(bc2)};
+    int cur = 0;   // grad[cur] = gradient w.r.t. the output of layer l
+    for (int l = 3; l >= 0; l--) {
+        const int K = tr_K(t, l), N = tr_N(l);
+        const float* in = l == 0 ? x : t->act[l - 1];
+        if (l > 0) {   // gradient w.r.t. this layer's input, through the ReLU that produced it, with the weights of BEFORE the update
+            mt::linear_bwd_data_kernel<<<(K + 7) / 8, 256, 0, st>>>(t->grad[cur], t->W[l], t->actT[l - 1], K, N, t->grad[cur ^ 1]);
+            CK_LAUNCH("linear_bwd_data_kernel");
+        }
+        mt::linear_bwd_weight_adam_kernel<<<dim3((K + 255) / 256, (N + mt::WN - 1) / mt::WN), 256, 0, st>>>(
+            t->grad[cur], in, B, K, N, t->W[l], t->mW[l], t->vW[l], t->b[l], t->mb[l], t->vb[l], a);
+        CK_LAUNCH("linear_bwd_weight_adam_kernel");
+        cur ^= 1;
+    }
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_trainer_forward(pfr_mlp_trainer_t t, const float* x, int n, float* out, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!t || !x || !out || n < 0) return PFR_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int r0 = 0; r0 < n; r0 += mt::MAXB) {
+        const int B = n - r0 < mt::MAXB ? n - r0 : mt::MAXB;
+        const int rc = trainer_forward32(t, x + (size_t)r0 * t->in_dim, B, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + (size_t)r0 * mt::OUT, t->act[3], (size_t)B * mt::OUT * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_trainer_loss(pfr_mlp_trainer_t t, const float* x, const float* y, int B, float* loss, void* stream) {
+    if (!t || !x || !y || !loss || B < 1 || B > mt::MAXB) return PFR_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = trainer_forward32(t, x, B, st);
+    if (rc) return rc;
+    mt::mse_kernel<<<1, 1024, 0, st>>>(t->act[3], y, B, mt::OUT, nullptr, loss);
+    CK_LAUNCH("mse_kernel");
+    return PFR_OK;
+}
+
+extern "C" int pfr_mlp_trainer_read(pfr_mlp_trainer_t t, float* const weights[4], float* const biases[4]) {
+    if (!t || !weights || !biases) return PFR_EINVAL;
+    CK(cudaDeviceSynchronize());
+    for (int l = 0; l < 4; l++) {
+        CK(cudaMemcpy(weights[l], t->W[l], (size_t)tr_N(l) * tr_K(t, l) * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(biases[l], t->b[l], (size_t)tr_N(l) * 4, cudaMemcpyDeviceToHost));
+    }
     return PFR_OK;
 }
 
