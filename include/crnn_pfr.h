@@ -46,6 +46,9 @@ extern "C" {
 #define PFR_METHOD_BS23 4       /* explicit Bogacki-Shampine 3(2), one thread per condition, knot-limited (tgrid required): the
                                  * fast path for the non-stiff knot intervals of the coupled (Eon) path; a condition that turns
                                  * out stiff stops with PFR_ST_STIFF */
+#define PFR_METHOD_DP54 5       /* explicit Dormand-Prince 5(4), one thread per condition, free stepping to t_end at T = T0 (tgrid,
+                                 * Tprof, idx_end, y_dense must be NULL): the fast path of the isothermal (Eoff) sweep; our own
+                                 * step-size controller, NOT torchdiffeq's (that is PFR_METHOD_DOPRI5); PFR_ST_STIFF as above */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;

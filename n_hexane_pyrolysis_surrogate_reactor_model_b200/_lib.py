@@ -14,6 +14,7 @@ METHOD_DOPRI5 = 1
 METHOD_RODAS4_TPC = 2
 METHOD_ROS3 = 3
 METHOD_BS23 = 4
+METHOD_DP54 = 5
 ST_STIFF = 4
 STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow",
                4: "stiff for the explicit fast path (integrate with ros3 / rodas4)"}

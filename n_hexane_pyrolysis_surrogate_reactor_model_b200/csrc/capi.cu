@@ -526,6 +526,28 @@ static int dispatch_bs23(const CrnnParams<real>& p, const RodasArgs& a0, cudaStr
 }
 
 template <typename real>
+static int dispatch_dp54(const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
+    if (!g_bs23_counters) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaMalloc(&g_bs23_counters, BS23_COUNTER_RING * sizeof(int)));
+    }
+    static bool configured = false;   // per template instantiation
+    if (!configured) {
+        CK(cudaFuncSetAttribute(dp54_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp54_smem_bytes<real>()));
+        configured = true;
+    }
+    RodasArgs a = a0;
+    a.work_counter = g_bs23_counters + (g_bs23_next++ % BS23_COUNTER_RING);
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+    const int full = (a.n + DP54_BLOCK - 1) / DP54_BLOCK, persistent = DP54_CTAS_PER_SM * g_num_sms;
+    dp54_kernel<real><<<full < persistent ? full : persistent, DP54_BLOCK, dp54_smem_bytes<real>(), st>>>(p, a);
+    CK_LAUNCH("dp54_kernel");
+    return PFR_OK;
+}
+
+template <typename real>
 static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaStream_t st) {
     const int grid = (a.n + DOPRI_BLOCK - 1) / DOPRI_BLOCK;
     if (a.Tprof) dopri5_kernel<real, true><<<grid, DOPRI_BLOCK, 0, st>>>(p, a);
@@ -540,7 +562,8 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
-    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 && method != PFR_METHOD_BS23) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 && method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54) return PFR_EINVAL;
+    if (method == PFR_METHOD_DP54 && (tgrid || !t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;   // isothermal outlet at t_end only
     if (method == PFR_METHOD_BS23 && !tgrid) return PFR_EINVAL;   // the explicit fast path is the knot-limited stepper
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
@@ -558,6 +581,10 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (method == PFR_METHOD_ROS3) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
         return precision == 64 ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
+    }
+    if (method == PFR_METHOD_DP54) {
+        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
+        return precision == 64 ? dispatch_dp54<double>(m->pd, a, st) : dispatch_dp54<float>(m->pf, a, st);
     }
     if (method == PFR_METHOD_BS23) {
         RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};

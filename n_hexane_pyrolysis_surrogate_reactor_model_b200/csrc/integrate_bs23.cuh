@@ -31,6 +31,12 @@
 
 namespace pfr {
 
+#ifndef PFR_BS23_KINK
+#define PFR_BS23_KINK 0     // error margin demanded of a step that straddles the kink of the lower state clamp; 0 = off.
+                            // Measured with 100 (2^20 LHS conditions, 1e-8): median outlet error 2.1e-7 -> 6.1e-8, p99 3.2e-6 ->
+                            // 1.2e-6, max unchanged, kernel +7 % (LLNL) ... +16 % of the step (JetSurf): the knot-limited steps
+                            // are short enough without it, so it is left off; the free-stepping dp54_kernel needs it.
+#endif
 constexpr int BS23_BLOCK = 128;
 #ifndef PFR_BS23_MINB
 #define PFR_BS23_MINB 2   // CTAs per SM.  2: 250 registers, no spills, 8 warps / SM; 3 (168 registers, 94 B of spills): 30 % slower
@@ -95,43 +101,40 @@ __device__ __forceinline__ int bound_key(float b) { return __float_as_int(fabsf(
 __device__ __forceinline__ bool maybe_outside(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) >= thr; }
 __device__ __forceinline__ bool maybe_outside(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) >= thr; }
 
-// du = f(T, y): streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
+// Temperature part of the exponents: kT_j = lnA_j - Ea_j / (R T) + b_j ln T
+template <typename real>
+__device__ __forceinline__ void arrhenius_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, real T, real (&kT)[NR]) {
+    const real invT = rcp_full(T);
+    const real mE = -p.inv_R * invT;
+    const real lnT = t_log<real>(T, sc.ft);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        real Ea, b, lnA, pad;
+        lds2(&sc.arr[j][0], Ea, b, lnT);
+        lds2(&sc.arr[j][2], lnA, pad, lnT);
+        kT[j] = fma(Ea, mE, fma(b, lnT, lnA));
+    }
+}
+
+// du = f(y) at given kT: streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
 // min(|zlo|, |zhi|) and min(|dulo|, |duhi|): the exponent and output clamps are skipped when no entry comes near them.
 template <typename real>
-__device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, real T,
-                                        const real (&y)[NS], real (&du)[NS]) {
+__device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, const real (&kT)[NR],
+                                           const real (&y)[NS], real (&du)[NS]) {
     real z[NR];
-    {
-        const real invT = rcp_full(T);
-        const real mE = -p.inv_R * invT;
-        const real lnT = t_log<real>(T, sc.ft);
 #pragma unroll
-        for (int j = 0; j < NR; j++) {
-            real Ea, b, lnA, pad;
-            lds2(&sc.arr[j][0], Ea, b, lnT);
-            lds2(&sc.arr[j][2], lnA, pad, lnT);
-            z[j] = fma(Ea, mE, fma(b, lnT, lnA));
-        }
-    }
+    for (int j = 0; j < NR; j++) z[j] = kT[j];
 #pragma unroll
     for (int k = 0; k < NS; k++) {
         const real l = t_log<real>(m_min(m_max(y[k], p.lb), p.ub), sc.ft);
         real c[10];
-#ifdef BS_CONSTBANK
-#pragma unroll
-        for (int j = 0; j < NR; j++) c[j] = p.nu[k][j];
-#else
         lds9(sc.nu[k], c, l);
-#endif
 #pragma unroll
         for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
     }
     bool near = false;
 #pragma unroll
     for (int j = 0; j < NR; j++) near = near || maybe_outside(z[j], zthr);
-#ifdef BS_NOBRANCH
-    near = true;
-#endif
     if (near) {
 #pragma unroll
         for (int j = 0; j < NR; j++) z[j] = m_min(m_max(z[j], p.zlo), p.zhi);
@@ -142,32 +145,32 @@ __device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef
     for (int j = 0; j < NR; j++) {
         const real r = t_exp<real>(z[j], sc.ft);
         real c[10];
-#ifdef BS_CONSTBANK
-#pragma unroll
-        for (int i = 0; i < NS; i++) c[i] = p.wout[i][j];
-#else
         lds9(sc.woutT[j], c, r);
-#endif
 #pragma unroll
         for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
     }
     near = false;
 #pragma unroll
     for (int i = 0; i < NS; i++) near = near || maybe_outside(du[i], dthr);
-#ifdef BS_NOBRANCH
-    near = true;
-#endif
     if (near) {
 #pragma unroll
         for (int i = 0; i < NS; i++) du[i] = m_min(m_max(du[i], p.dulo), p.duhi);
     }
 }
 
-template <typename real, bool kRamp>
-__global__ void __launch_bounds__(BS23_BLOCK, PFR_BS23_MINB)
-bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
-    __shared__ __align__(16) TpcCoef<real> sc;
-    for (int e = threadIdx.x; e < NS * 10; e += BS23_BLOCK) {
+// du = f(T, y)
+template <typename real>
+__device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, real T,
+                                        const real (&y)[NS], real (&du)[NS]) {
+    real kT[NR];
+    arrhenius_tpc<real>(p, sc, T, kT);
+    rhs_tpc_kT<real>(p, sc, zthr, dthr, kT, y, du);
+}
+
+// block-shared copy of the coefficients and tables (every kernel of this file starts with it)
+template <typename real, int kBlock>
+__device__ __forceinline__ void load_tpc_coef(TpcCoef<real>& sc, const CrnnParams<real>& p, const FastTables* tables) {
+    for (int e = threadIdx.x; e < NS * 10; e += kBlock) {
         const int r = e / 10, c = e % 10;
         sc.nu[r][c] = c < NR ? p.nu[r][c] : real(0);
         sc.woutT[r][c] = c < NS ? p.wout[c][r] : real(0);
@@ -179,10 +182,17 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
         sc.arr[threadIdx.x][3] = real(0);
     }
     if (sizeof(real) == 8) {
-        for (int e = threadIdx.x; e < LOGTAB_N; e += BS23_BLOCK) sc.ft.logtab[e] = a.tables->logtab[e];
-        for (int e = threadIdx.x; e < EXPTAB_N; e += BS23_BLOCK) sc.ft.exptab[e] = a.tables->exptab[e];
+        for (int e = threadIdx.x; e < LOGTAB_N; e += kBlock) sc.ft.logtab[e] = tables->logtab[e];
+        for (int e = threadIdx.x; e < EXPTAB_N; e += kBlock) sc.ft.exptab[e] = tables->exptab[e];
     }
     __syncthreads();
+}
+
+template <typename real, bool kRamp>
+__global__ void __launch_bounds__(BS23_BLOCK, PFR_BS23_MINB)
+bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+    __shared__ __align__(16) TpcCoef<real> sc;
+    load_tpc_coef<real, BS23_BLOCK>(sc, p, a.tables);
     const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
     const int lane = threadIdx.x & 31;
     const size_t n = (size_t)a.n;
@@ -300,7 +310,17 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 d1 = fma(k2[k] * isk, k2[k] * isk, d1);
                 finite = finite && (m_abs(w[k]) < real(1e30));
             }
-            const real err = m_sqrt<real>(e2 / real(NS));
+            real err = m_sqrt<real>(e2 / real(NS));
+#if PFR_BS23_KINK
+            {   // A step during which a species crosses the lower state clamp straddles a kink of the right-hand side
+                // (ln max(y, lb)); the embedded estimate, built for smooth f, under-reports the error there.  Such a step has
+                // to meet the tolerance with a margin, which shrinks it until the kink is crossed with a small h.
+                bool crossed = false;
+#pragma unroll
+                for (int k = 0; k < NS; k++) crossed = crossed || ((y[k] < p.lb) != (w[k] < p.lb));
+                if (crossed) err *= real(PFR_BS23_KINK);
+            }
+#endif
             finite = finite && (err == err) && (err < real(1e30));
             const float fac = 0.9f / cbrtf(fmaxf((float)err, 1e-30f));
             if (fresh) {
@@ -369,6 +389,175 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 for (int kk = kc + 1; kk < NTOT; kk++)
 #pragma unroll
                     for (int k = 0; k < NS; k++) y_dense[((size_t)kk * NS + k) * n + i] = raw ? y[k] : yf[k];
+            }
+            have = false;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Free-stepping explicit integrator for the ISOTHERMAL sweep (Eoff: T = T0, integrate to t_end, no knots): Dormand-Prince 5(4)
+// with FSAL, one condition per thread, same work queue / coefficient broadcast / clamp tests as bs23_kernel.
+//
+// The isothermal problem is as non-stiff as the coupled one (the reference's dopri5 takes 3-36 accepted steps for it), and
+// here the error -- not a knot grid -- sets the step, so a 5th-order pair pays: ~100 right-hand sides per trajectory
+// against RODAS4's ~180 plus 30 Jacobians and inversions, and a warp instruction serves 32 conditions instead of 10.
+// The seven stage slopes live in shared memory ([stage][species][thread], conflict-free), which lets the stages run as a
+// ROLLED loop over the tableau (one copy of the right-hand side in the instruction stream) without indexing registers
+// dynamically.  kT_j is constant along a trajectory and is hoisted.  The controller follows the Rosenbrock kernels (RMS
+// norm against atol + rtol max(|y0|, |y1|), factor clip(0.9 err^(-1/5), 0.2, 6), last step clipped to t_end); a condition
+// that needs more than DP54_MAX_ATTEMPTS attempts stops with PFR_ST_STIFF and is handed to RODAS4 by the host.
+#ifndef PFR_DP54_KINK
+#define PFR_DP54_KINK 1000   // as PFR_BS23_KINK; free steps are long, the margin matters more: at 1e-7 the p99 error falls 500x
+#endif
+constexpr int DP54_BLOCK = 128, DP54_CTAS_PER_SM = 2, DP54_STAGES = 7, DP54_MAX_ATTEMPTS = 2000;
+template <typename real> constexpr size_t dp54_smem_bytes() { return (size_t)DP54_STAGES * NS * DP54_BLOCK * sizeof(real); }
+
+struct Dp54Tableau {
+    double a[DP54_STAGES][DP54_STAGES - 1];   // row s: coefficients of k_0 .. k_{s-1}; row 6 = the 5th-order weights (FSAL)
+    double e[DP54_STAGES];                    // error weights b - b*
+};
+__constant__ Dp54Tableau c_dp54 = {
+    {{0, 0, 0, 0, 0, 0},
+     {1.0 / 5, 0, 0, 0, 0, 0},
+     {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+     {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+     {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+     {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}},
+    {35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720, -2187.0 / 6784 + 12231.0 / 42400,
+     11.0 / 84 - 649.0 / 6300, -1.0 / 60}};
+
+template <typename real>
+__global__ void __launch_bounds__(DP54_BLOCK, DP54_CTAS_PER_SM)
+dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+    __shared__ __align__(16) TpcCoef<real> sc;
+    extern __shared__ __align__(16) unsigned char dp_dyn[];
+    real* const ks = reinterpret_cast<real*>(dp_dyn) + threadIdx.x;   // slope k_s of species i: ks[(s * NS + i) * DP54_BLOCK]
+    load_tpc_coef<real, DP54_BLOCK>(sc, p, a.tables);
+    const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)a.n;
+    real* __restrict__ y_out = static_cast<real*>(a.y_out);
+    const real rtol = real(a.rtol), atol = real(a.atol);
+
+    bool have = false, fresh = false, exhausted = false;
+    int i = 0, nacc = 0, nrej = 0, nrhs = 0, status = 0;
+    double t = 0.0, t_final = 0.0, hprop = 0.0;
+    real y[NS], kT[NR];
+#pragma unroll
+    for (int k = 0; k < NS; k++) y[k] = real(0);
+#pragma unroll
+    for (int j = 0; j < NR; j++) kT[j] = real(0);
+
+    while (true) {
+        const unsigned want = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (want) {
+            int base = 0;
+            const int leader = __ffs(want) - 1;
+            if (lane == leader) base = atomicAdd(a.work_counter, __popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have && !exhausted) {
+                const int slot = base + __popc(want & ((1u << lane) - 1u));
+                if (slot >= a.n) {
+                    exhausted = true;
+                } else {
+                    i = a.perm ? a.perm[slot] : slot;
+#pragma unroll
+                    for (int k = 0; k < NS; k++) y[k] = real(0);
+                    y[NS - 3] = real(a.c0[i]);
+                    t = 0.0;
+                    t_final = (double)a.t_end[i];
+                    nacc = nrej = nrhs = status = 0;
+                    hprop = 0.0;
+                    have = true;
+                    fresh = t_final > t;
+                    if (fresh) arrhenius_tpc<real>(p, sc, real(a.T0[i]), kT);
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !have)) break;
+        bool done = have && !fresh && !(t_final > t);
+        if (have && !done) {
+            // a new condition enters with a zero-length step that runs stage 0 only: f(y0) for the first-step guess and FSAL
+            const double dist = t_final - t;
+            const bool clip = !fresh && hprop * 1.01 >= dist;
+            const double hs = fresh ? 0.0 : (clip ? dist : hprop);
+            const real h = real(hs);
+            real w[NS], f[NS];
+#pragma unroll 1
+            for (int s = fresh ? 0 : 1; s < (fresh ? 1 : DP54_STAGES); s++) {
+#pragma unroll
+                for (int k = 0; k < NS; k++) w[k] = real(0);
+                for (int j = 0; j < s; j++) {
+                    const real c = real(c_dp54.a[s][j]);
+#pragma unroll
+                    for (int k = 0; k < NS; k++) w[k] = fma(c, ks[(j * NS + k) * DP54_BLOCK], w[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < NS; k++) w[k] = fma(h, w[k], y[k]);
+                rhs_tpc_kT<real>(p, sc, zthr, dthr, kT, w, f);
+#pragma unroll
+                for (int k = 0; k < NS; k++) ks[(s * NS + k) * DP54_BLOCK] = f[k];
+            }
+            nrhs += fresh ? 1 : DP54_STAGES - 1;
+            // w = y1 (row 6 of the tableau = the 5th-order weights), f = f(y1)   [entry step: w = y0, f = f(y0), h = 0]
+            real e2 = real(0), d0 = real(0), d1 = real(0);
+            bool finite = true;
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                real ek = real(0);
+#pragma unroll
+                for (int j = 0; j < DP54_STAGES; j++) ek = fma(real(c_dp54.e[j]), ks[(j * NS + k) * DP54_BLOCK], ek);
+                ek *= h;
+                const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
+                e2 = fma(ek * isk, ek * isk, e2);
+                d0 = fma(y[k] * isk, y[k] * isk, d0);
+                d1 = fma(f[k] * isk, f[k] * isk, d1);
+                finite = finite && (m_abs(w[k]) < real(1e30));
+            }
+            real err = m_sqrt<real>(e2 / real(NS));
+            // A step during which a species crosses the lower state clamp straddles a kink of the right-hand side
+            // (ln max(y, lb)); the embedded estimate, built for smooth f, under-reports the error there.  Such a step has to
+            // meet the tolerance with a margin of PFR_DP54_KINK, which shrinks it until the kink is crossed with a small h.
+            bool crossed = false;
+#pragma unroll
+            for (int k = 0; k < NS; k++) crossed = crossed || ((y[k] < p.lb) != (w[k] < p.lb));
+            if (crossed) err *= real(PFR_DP54_KINK);
+            finite = finite && (err == err) && (err < real(1e30));
+            const float fac = 0.9f * __powf(fmaxf((float)err, 1e-30f), -0.2f);
+            if (fresh) {
+                d0 = m_sqrt<real>(d0 / real(NS));
+                d1 = m_sqrt<real>(d1 / real(NS));
+                const double h0 = (d0 < real(1e-5) || d1 < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
+                hprop = fmin(100.0 * h0, t_final - t);
+                fresh = false;
+#pragma unroll
+                for (int k = 0; k < NS; k++) ks[k * DP54_BLOCK] = f[k];
+            } else if (finite && err <= real(1)) {
+                const double g = fmin(6.0, fmax(0.2, (double)fac));
+                hprop = clip ? fmax(hprop, hs * g) : hs * g;
+                nacc++;
+#pragma unroll
+                for (int k = 0; k < NS; k++) { y[k] = w[k]; ks[k * DP54_BLOCK] = f[k]; }
+                if (clip) { t = t_final; done = true; } else { t += hs; }
+            } else {
+                nrej++;
+                const double g = finite ? fmax(0.2, (double)fac) : 0.2;
+                hprop = hs * fmin(g, 0.9);
+                if (!(t + hprop > t) || hprop < 1e-300) { status = finite ? PFR_ST_UNDERFLOW_ : PFR_ST_NONFINITE_; done = true; }
+            }
+            if (!done && nacc + nrej > DP54_MAX_ATTEMPTS) { status = PFR_ST_STIFF_; done = true; }
+            if (!done && nacc + nrej >= a.max_steps) { status = PFR_ST_MAXSTEPS_; done = true; }
+        }
+        if (done) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) y_out[(size_t)k * n + i] = m_min(m_max(y[k], p.lb), p.ub);
+            a.status[i] = status;
+            if (a.stats) {
+                a.stats[i] = nacc;
+                a.stats[n + i] = nrej;
+                a.stats[2 * n + i] = nrhs;
             }
             have = false;
         }

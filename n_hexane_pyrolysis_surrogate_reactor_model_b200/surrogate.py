@@ -30,7 +30,7 @@ INFERENCE_CLAMPS = (1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # ...Eon_singl
 TRAINING_WIDE_CLAMPS = (1.0e-6, 6.0e1, -1.0e1, 1.0e1, -1.0e5, 1.0e5)  # WIDE_Eoff_surrogate_model_training.py:39-53
 TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eoff_surrogate_model_training.py:40-43,54
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
-           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23}
+           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54}
 
 
 def _ptr(t):
@@ -222,7 +222,7 @@ class Surrogate:
                   precision=64, rtol=1e-6, atol=1e-6, dense=False, max_steps=0, dense_raw=False, stiff_fallback="ros3") -> SolveResult:
         """pfr_integrate on device arrays.  method: "rodas4" (6-stage Rosenbrock), "ros3" (3-stage Rosenbrock), "bs23" (explicit
         knot-limited fast path; conditions it flags as stiff are re-integrated with `stiff_fallback`, None to leave them
-        flagged), "rodas4_tpc" (cross-check mapping), "dopri5" (reference-behaviour mode)."""
+        flagged), "dp54" (explicit free-stepping fast path of the isothermal sweep, t_end only; stiff conditions go to rodas4), "rodas4_tpc" (cross-check mapping), "dopri5" (reference-behaviour mode)."""
         T0, c0 = _f32(T0, self.device), _f32(c0, self.device)
         n = T0.numel()
         dt = torch.float64 if precision == 64 else torch.float32
@@ -234,8 +234,9 @@ class Surrogate:
                                             _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
         res = SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
-        if method == "bs23" and stiff_fallback:
-            self._integrate_stiff_remainder(res, T0, c0, stiff_fallback, precision, rtol, atol, max_steps, dense_raw)
+        if method in ("bs23", "dp54") and stiff_fallback:
+            self._integrate_stiff_remainder(res, T0, c0, "rodas4" if method == "dp54" else stiff_fallback, precision, rtol, atol,
+                                            max_steps, dense_raw)
         return res
 
     def _integrate_stiff_remainder(self, res, T0, c0, method, precision, rtol, atol, max_steps, dense_raw):
@@ -246,7 +247,8 @@ class Surrogate:
         if not bool(stiff.any()):
             return
         sel = stiff.nonzero().flatten()
-        sub = self.integrate(T0[sel], c0[sel], tgrid=res.tgrid[:, sel].contiguous(),
+        sub = self.integrate(T0[sel], c0[sel], tgrid=None if res.tgrid is None else res.tgrid[:, sel].contiguous(),
+                             t_end=None if res.tgrid is not None or res.t_end is None else res.t_end[sel].contiguous(),
                              Tprof=None if res.Tprof is None else res.Tprof[:, sel].contiguous(),
                              idx_end=None if res.idx_cut is None else res.idx_cut[sel].contiguous(), method=method,
                              precision=precision, rtol=rtol, atol=atol, dense=res.dense is not None, max_steps=max_steps,

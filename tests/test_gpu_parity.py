@@ -334,6 +334,48 @@ def test_bs23_stiff_guard_hands_over_to_rosenbrock(surrogates, golden):
     assert np.max(rel_err(auto.y.cpu().numpy().T, tight.y.cpu().numpy().T)) < 1e-3
 
 
+def test_dp54_isothermal_fast_path(surrogates, golden, conditions):
+    """The explicit free-stepping fast path of the isothermal sweep (PFR_METHOD_DP54): within 1e-6 of the converged oracle
+    solution at rtol = atol = 1e-10; at the tolerance the bench runs it with (1e-7) closer to it than RODAS4 at the
+    reference's 1e-6; rhs = 6 x attempts + 1; ragged batches bit-identical to the full batch (work queue); and a 2000x longer
+    residence time at 1150 K trips the stiffness guard, after which the host hands those conditions to RODAS4."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    s = surrogates("LLNL", "Eoff")
+    tend = torch.as_tensor(golden["Eoff/tgrid"][:, -1].copy()).cuda()
+    truth = np.clip(golden["Eoff/truth_outlet"], 1e-6, 60.0)
+    T0, c0 = golden["T"], golden["c0"][:, 6]
+    tight = s.integrate(T0, c0, t_end=tend, method="dp54", rtol=1e-10, atol=1e-10, stiff_fallback=None)
+    assert int(tight.status.abs().sum()) == 0
+    st = tight.stats.cpu().numpy()
+    assert np.array_equal(st[2], 6 * (st[0] + st[1]) + 1)
+    e_tight = np.max(rel_err(tight.y.cpu().numpy().T, truth))
+    bench = s.integrate(T0, c0, t_end=tend, method="dp54", rtol=1e-7, atol=1e-7)
+    rodas = s.integrate(T0, c0, t_end=tend, method="rodas4", rtol=1e-6, atol=1e-6)
+    e_bench, e_rodas = rel_err(bench.y.cpu().numpy().T, truth).max(), rel_err(rodas.y.cpu().numpy().T, truth).max()
+    print(f"dp54: tight {e_tight:.2e} ({(st[0] + st[1]).mean():.0f} attempts), 1e-7 {e_bench:.2e} "
+          f"({float(bench.stats[2].double().mean()):.0f} rhs), rodas4 1e-6 {e_rodas:.2e} ({float(rodas.stats[2].double().mean()):.0f} rhs)")
+    assert e_tight < 1e-6 and e_bench <= e_rodas
+    # 400 shipped conditions: ragged sub-batches equal the full batch bit for bit
+    T, P, L, U = cond4(conditions)
+    full = s.sweep(T, P, L, U, method="dp54", rtol=1e-7, atol=1e-7, sort=False)
+    assert int(full.status.abs().sum()) == 0 and full.stiff_fallbacks == 0
+    cc = s.inlet_concentration(T, P)
+    for m in (1, 31, 33, 129):
+        sub = s.integrate(T[:m], cc[:m], t_end=full.t_end[:m].contiguous(), method="dp54", rtol=1e-7, atol=1e-7)
+        assert torch.equal(sub.y, full.y[:, :m]) and torch.equal(sub.stats, full.stats[:, :m])
+    ref = s.sweep(T, P, L, U, method="rodas4", rtol=1e-11, atol=1e-11).y
+    assert float(((full.y - ref).abs() / ref.abs().clamp(min=1e-3)).max()) < 2e-5
+    # stiffness guard
+    hot = np.full(16, 1150.0, np.float32)
+    bare = s.integrate(hot, c0, t_end=tend * 2000.0, method="dp54", rtol=1e-6, atol=1e-6, stiff_fallback=None)
+    flagged = bare.status == _lib.ST_STIFF
+    assert int(flagged.sum()) > 0 and int(((bare.status != 0) & ~flagged).sum()) == 0
+    auto = s.integrate(hot, c0, t_end=tend * 2000.0, method="dp54", rtol=1e-6, atol=1e-6)
+    ros = s.integrate(hot, c0, t_end=tend * 2000.0, method="rodas4", rtol=1e-6, atol=1e-6)
+    assert int(auto.status.abs().sum()) == 0 and auto.stiff_fallbacks == int(flagged.sum())
+    assert torch.equal(auto.y[:, flagged], ros.y[:, flagged])
+
+
 def test_rodas_fp32_state(surrogates, golden):
     s = surrogates("LLNL", "Eoff")
     tg, _, _ = _grids(golden, "Eoff")

@@ -51,7 +51,7 @@ def main():
             run = lambda meth, tol: s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, method=meth, rtol=tol, atol=tol)
         ref = run("rodas4", 1e-11).y.clone()
         scale = torch.clamp(ref.abs(), min=1e-3)
-        for meth in methods:
+        for meth in (m for m in methods if not (variant == "Eon" and m == "dp54") and not (variant == "Eoff" and m == "bs23")):
             for tol in (1e-5, 1e-6, 1e-7, 3e-8, 1e-8, 1e-9):
                 ms, res = timed(lambda: run(meth, tol))
                 e = ((res.y - ref).abs() / scale).amax(0)
