@@ -241,6 +241,18 @@ def run_ours(args, emit=print):
                 accuracy[nm] = {"rtol": k2["rtol"], "atol": k2["atol"], "max": float(e.max()), "p99": float(torch.quantile(e, 0.99)),
                                 "median": float(e.median())}
             del yref, scale
+        acc_eoff = None
+        if variant == "Eoff" and method == "dp54" and rank == 0:
+            sel = torch.arange(0, n, 16, device=dev)
+            sub = lambda **k2: sur.integrate(T[sel], c0[sel], t_end=tend[sel].contiguous(), precision=64, **k2).y
+            yref = sub(method="rodas4", rtol=1e-11, atol=1e-11)
+            scale = torch.clamp(yref.abs(), min=1e-3)
+            acc_eoff = {"reference_solution": "RODAS4 at rtol = atol = 1e-11", "conditions": int(sel.numel())}
+            for nm, k2 in (("dp54", dict(method="dp54", rtol=rtol, atol=atol)),
+                           ("rodas4_at_reference_tolerances", dict(method="rodas4", rtol=args.rtol, atol=args.atol))):
+                e = ((sub(**k2) - yref).abs() / scale).amax(0)
+                acc_eoff[nm] = {"rtol": k2["rtol"], "atol": k2["atol"], "max": float(e.max()), "p99": float(torch.quantile(e, 0.99)),
+                                "median": float(e.median())}
         entry = {
             "value": n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps,
             "e2e": n_total * steps / (ms_e2e * 1e-3), "failed_trajectories": bad, "work_per_trajectory": work,
@@ -248,6 +260,8 @@ def run_ours(args, emit=print):
             "integrator_ms": kms, "integrator_ms_timed_alone": kms_alone, "integrator_share_of_step": kms / (ms / steps),
             "integrator_fp64_tflops": flops / (kms * 1e-3) / 1e12, "stiff_fallbacks": int(getattr(res, "stiff_fallbacks", 0)),
         }
+        if acc_eoff:
+            entry["accuracy"] = acc_eoff
         entry["mlp_arithmetic"] = mlp_mode
         entry["integrator"], entry["rtol"], entry["atol"] = method, rtol, atol
         variants[f"LLNL_{variant}" + ("" if headline or method == "dp54" else f"_{method}") + ("" if mlp_mode == "tf32x3" else "_mlp_fp32")] = entry

@@ -306,47 +306,84 @@ static int launch_tc_gemm(const CUtensorMap& ahi, const CUtensorMap& alo, const 
     return PFR_OK;
 }
 
+// Auxiliary streams for the two-lane chunk pipeline of mlp_run_tc (round robin over calls, so that concurrent passes on
+// different caller streams do not queue behind each other on one auxiliary stream)
+static cudaStream_t g_mlp_aux[4] = {nullptr, nullptr, nullptr, nullptr};
+static int g_mlp_aux_next = 0;
+
+// Chunks alternate between two lanes (each with its own activation buffers, half of the workspace): lane 0 runs on the
+// caller's stream, lane 1 on an auxiliary stream forked from / joined to it by events.  The GEMM kernels of the two lanes
+// take the SMs in turn (one persistent CTA per SM with ~210 KB of shared memory), while the HBM-bound kernels of one lane
+// (first layer, enforce_strict) run beside the other lane's GEMM CTAs instead of in front of them.
 static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
-                      float* t_end, bool is_time, int raw, float* H, float* S, int ld, cudaStream_t st) {
-    float* Ahi = H;
-    float* Alo = H + (size_t)MLP_HID * ld;
-    float* Bhi = H + (size_t)2 * MLP_HID * ld;
-    float* Blo = H + (size_t)3 * MLP_HID * ld;
-    CUtensorMap mA[2][2];
+                      float* t_end, bool is_time, int raw, float* H, float* S, int ld_full, cudaStream_t st) {
+    const bool two = n > ld_full / 2 && ld_full % (2 * tc::BM) == 0;
+    const int ld = two ? ld_full / 2 : ld_full;
+    const int lanes = two ? 2 : 1;
+    CUtensorMap mA[2][2][2];
+    float *Ahi[2], *Alo[2], *Bhi[2], *Blo[2], *Sl[2];
     int rc;
-    if ((rc = make_map_2d(&mA[0][0], Ahi, ld, tc::BM)) || (rc = make_map_2d(&mA[0][1], Alo, ld, tc::BM)) ||
-        (rc = make_map_2d(&mA[1][0], Bhi, ld, tc::BM)) || (rc = make_map_2d(&mA[1][1], Blo, ld, tc::BM)))
-        return rc;
+    for (int l = 0; l < lanes; l++) {
+        float* Hl = H + (size_t)l * 4 * MLP_HID * ld;
+        Ahi[l] = Hl;
+        Alo[l] = Hl + (size_t)MLP_HID * ld;
+        Bhi[l] = Hl + (size_t)2 * MLP_HID * ld;
+        Blo[l] = Hl + (size_t)3 * MLP_HID * ld;
+        Sl[l] = S + (size_t)l * MLP_OUT * ld;
+        if ((rc = make_map_2d(&mA[l][0][0], Ahi[l], ld, tc::BM)) || (rc = make_map_2d(&mA[l][0][1], Alo[l], ld, tc::BM)) ||
+            (rc = make_map_2d(&mA[l][1][0], Bhi[l], ld, tc::BM)) || (rc = make_map_2d(&mA[l][1][1], Blo[l], ld, tc::BM)))
+            return rc;
+    }
+    cudaStream_t lane_stream[2] = {st, st};
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (two) {
+        cudaStream_t& aux = g_mlp_aux[g_mlp_aux_next++ & 3];
+        if (!aux) CK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        lane_stream[1] = aux;
+        CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        CK(cudaEventRecord(fork, st));
+        CK(cudaStreamWaitEvent(aux, fork, 0));
+    }
     const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
-    for (int c0 = 0; c0 < n; c0 += ld) {
+    int ci = 0;
+    for (int c0 = 0; c0 < n; c0 += ld, ci++) {
+        const int l = ci % lanes;
+        cudaStream_t ls = lane_stream[l];
         const int mv = (n - c0) < ld ? (n - c0) : ld;
         const int rows = round_up(mv, tc::BM);
-        tc::mlp_tc_layer1_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, st>>>(   // 8 warps per block, 8 rows per warp
+        tc::mlp_tc_layer1_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ls>>>(   // 8 warps per block, 8 rows per warp
             m->W1, m->b1, m->in_dim, m->sc.lo[0], m->sc.lo[1], m->sc.lo[2], m->sc.lo[3], m->sc.span[0], m->sc.span[1],
             m->sc.span[2], m->sc.span[3], m->sc.fullL, m->sc.fullU, T + c0, P + c0, L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv,
-            rows, Ahi, Alo);
+            rows, Ahi[l], Alo[l]);
         CK_LAUNCH("mlp_tc_layer1_kernel");
         const int mt = rows / tc::BM;
-        tc::GemmArgs g2{m->b2, Bhi, Blo, 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[0]};
-        if ((rc = launch_tc_gemm<false>(mA[0][0], mA[0][1], m->mapWhi[0], m->mapWlo[0], g2, st))) return rc;
-        tc::GemmArgs g3{m->b3, Ahi, Alo, 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[1]};
-        if ((rc = launch_tc_gemm<false>(mA[1][0], mA[1][1], m->mapWhi[1], m->mapWlo[1], g3, st))) return rc;
-        float* out_rows = grid ? grid + (size_t)n + c0 : S;
+        tc::GemmArgs g2{m->b2, Bhi[l], Blo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[0]};
+        if ((rc = launch_tc_gemm<false>(mA[l][0][0], mA[l][0][1], m->mapWhi[0], m->mapWlo[0], g2, ls))) return rc;
+        tc::GemmArgs g3{m->b3, Ahi[l], Alo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[1]};
+        if ((rc = launch_tc_gemm<false>(mA[l][1][0], mA[l][1][1], m->mapWhi[1], m->mapWlo[1], g3, ls))) return rc;
+        float* out_rows = grid ? grid + (size_t)n + c0 : Sl[l];
         const size_t out_ld = grid ? (size_t)n : (size_t)ld;
         tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin, (MLP_OUT + tc::BN - 1) / tc::BN, mt, g_tc_trace[2]};
-        if ((rc = launch_tc_gemm<true>(mA[0][0], mA[0][1], m->mapWhi[2], m->mapWlo[2], g4, st))) return rc;
+        if ((rc = launch_tc_gemm<true>(mA[l][0][0], mA[l][0][1], m->mapWhi[2], m->mapWlo[2], g4, ls))) return rc;
         if (is_time) {
             if (!raw) {
-                enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, st>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,
+                enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, ls>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,
                                                                         t_end ? t_end + c0 : nullptr, grid ? 1 : 0);
                 CK_LAUNCH("enforce_strict_kernel");
             } else if (grid) {
-                CK(cudaMemsetAsync(grid + c0, 0, (size_t)mv * sizeof(float), st));
+                CK(cudaMemsetAsync(grid + c0, 0, (size_t)mv * sizeof(float), ls));
             }
         } else {
-            copy_row_kernel<<<(mv + 255) / 256, 256, 0, st>>>(T + c0, grid + c0, mv);
+            copy_row_kernel<<<(mv + 255) / 256, 256, 0, ls>>>(T + c0, grid + c0, mv);
             CK_LAUNCH("copy_row_kernel");
         }
+    }
+    if (two) {
+        CK(cudaEventRecord(join, lane_stream[1]));
+        CK(cudaStreamWaitEvent(st, join, 0));
+        CK(cudaEventDestroy(fork));
+        CK(cudaEventDestroy(join));
     }
     return PFR_OK;
 }
