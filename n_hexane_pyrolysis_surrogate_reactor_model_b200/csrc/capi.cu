@@ -12,9 +12,9 @@
 #include "crnn_device.cuh"
 #include "integrate_dopri5.cuh"
 #include "integrate_rodas.cuh"
-#include "integrate_bs23.cuh"
+#include "integrate_explicit.cuh"
 #include "integrate_rodas_coop.cuh"
-#include "integrate_bs23.cuh"
+#include "integrate_explicit.cuh"
 #include "adjoint.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"

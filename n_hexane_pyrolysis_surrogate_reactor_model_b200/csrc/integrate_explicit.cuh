@@ -1,5 +1,6 @@
-// Explicit knot-limited integrator for the NON-STIFF regime of the CRNN plug-flow problem: Bogacki-Shampine 3(2)
-// with FSAL, one PFR condition per thread.
+// Explicit integrators for the NON-STIFF regime of the CRNN plug-flow problem, one PFR condition per thread:
+//   bs23_kernel  Bogacki-Shampine 3(2) with FSAL, knot-limited steps      (the coupled Eon sweep; described first)
+//   dp54_kernel  Dormand-Prince 5(4) with FSAL, free stepping to t_end    (the isothermal Eoff sweep; second half of the file)
 //
 // Why it exists.  On the coupled (Eon) path the temperature is the MLP's piecewise-linear profile and a step never
 // crosses one of its 801 knots (integrate_rodas.cuh explains why).  The knot spacing (median 5e-4 s) is then 10-50x

@@ -23,7 +23,7 @@ def main():
     off = Surrogate(ModelSet.from_packed(gold, "Eoff"))
     for _ in range(2):
         r1 = on.sweep(T, P, L, U, precision=prec, method=method, rtol=tol, atol=tol)
-        r2 = off.sweep(T, P, L, U, precision=prec)
+        r2 = off.sweep(T, P, L, U, precision=prec, method=os.environ.get("PFR_EOFF_METHOD", "rodas4"), rtol=float(os.environ.get("PFR_EOFF_TOL", "1e-6")), atol=float(os.environ.get("PFR_EOFF_TOL", "1e-6")))
     torch.cuda.synchronize()
     print("ok", float(r1.y.sum()), float(r2.y.sum()), int(r1.status.sum()), int(r2.status.sum()))
 
