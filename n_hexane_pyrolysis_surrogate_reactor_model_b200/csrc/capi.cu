@@ -437,6 +437,7 @@ static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, 
 
 extern "C" int pfr_time_grid(pfr_mlp_t mlp, const float* T, const float* P, const float* L, const float* u0, int n, float* tgrid,
                   float* t_end, int raw, void* workspace, size_t workspace_bytes, int chunk, void* stream) {
+    if (n == 0) return PFR_OK;
     if (!mlp || mlp->in_dim != 4) return PFR_EINVAL;
     if ((L == nullptr) != (u0 == nullptr)) return PFR_EINVAL;
     if (raw && !tgrid) return PFR_EINVAL;
@@ -445,6 +446,7 @@ extern "C" int pfr_time_grid(pfr_mlp_t mlp, const float* T, const float* P, cons
 
 extern "C" int pfr_temp_profile(pfr_mlp_t mlp, const float* T, const float* P, int n, float* Tprof, int raw, void* workspace,
                      size_t workspace_bytes, int chunk, void* stream) {
+    if (n == 0) return PFR_OK;
     if (!mlp || mlp->in_dim != 2 || !Tprof) return PFR_EINVAL;
     return mlp_run(mlp, T, P, nullptr, nullptr, n, Tprof, nullptr, false, raw, workspace, workspace_bytes, chunk,
                    (cudaStream_t)stream);

@@ -630,6 +630,42 @@ def test_empty_batch_and_bad_arguments(surrogates):
         s.temp_profile(np.ones(4, np.float32), np.ones(4, np.float32))   # Eoff has no temperature MLP
 
 
+def test_degenerate_conditions_every_integrator(surrogates, golden):
+    """Conditions with nothing to integrate (outlet knot 0, or t_end = 0) return the clamped inlet state with status 0 and
+    zero accepted steps in every integrator, next to ordinary conditions of the same batch; the fast paths refuse the
+    argument combinations they do not implement; empty batches are no-ops."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    s = surrogates("LLNL", "Eon")
+    tg = torch.as_tensor(golden["Eon/tgrid_full"].T.copy()).cuda()
+    Tp = torch.as_tensor(golden["Eon/Tprof"].T.copy()).cuda()
+    idx = torch.as_tensor(golden["Eon/idx_cut"].copy()).cuda()
+    idx[::3] = 0
+    T0, c0 = golden["T"], golden["c0"][:, 6]
+    inlet = np.full((16, 9), 1e-6)
+    inlet[:, 6] = c0
+    for method, prec in (("rodas4", 64), ("ros3", 64), ("bs23", 64), ("bs23", 32)):
+        r = s.integrate(T0, c0, tgrid=tg, Tprof=Tp, idx_end=idx, method=method, precision=prec, rtol=1e-6, atol=1e-6)
+        y, st = r.y.cpu().numpy().T, r.stats.cpu().numpy()
+        assert int(r.status.abs().sum()) == 0
+        assert np.allclose(y[::3], inlet[::3], rtol=1e-6) and np.all(st[0, ::3] == 0)
+        assert np.all(st[0, 1::3] > 0) and np.all(np.abs(y[1::3, 6] - c0[1::3]) > 1e-3)
+    soff = surrogates("LLNL", "Eoff")
+    tend = torch.as_tensor(golden["Eoff/tgrid"][:, -1].copy()).cuda()
+    tend[::3] = 0.0
+    for method, prec in (("rodas4", 64), ("dp54", 64), ("dp54", 32)):
+        r = soff.integrate(T0, c0, t_end=tend, method=method, precision=prec, rtol=1e-6, atol=1e-6)
+        y, st = r.y.cpu().numpy().T, r.stats.cpu().numpy()
+        assert int(r.status.abs().sum()) == 0
+        assert np.allclose(y[::3], inlet[::3], rtol=1e-6) and np.all(st[0, ::3] == 0) and np.all(st[0, 1::3] > 0)
+    with pytest.raises(_lib.PfrError):
+        soff.integrate(T0, c0, tgrid=tg, method="dp54")                  # dp54 is the t_end-only path
+    with pytest.raises(_lib.PfrError):
+        soff.integrate(T0, c0, t_end=tend, method="bs23")                # bs23 is the knot-limited path
+    e = np.zeros(0, np.float32)
+    for method in ("bs23", "dp54"):
+        assert (s if method == "bs23" else soff).sweep(e, e, e, e, method=method).y.shape == (9, 0)
+
+
 def test_status_reports_max_steps(surrogates, golden):
     s = surrogates("LLNL", "Eoff")
     tend = torch.as_tensor(golden["Eoff/tgrid"][:, -1].copy()).cuda()
