@@ -671,6 +671,11 @@ def test_degenerate_conditions_every_integrator(surrogates, golden):
     e = np.zeros(0, np.float32)
     for method in ("bs23", "dp54"):
         assert (s if method == "bs23" else soff).sweep(e, e, e, e, method=method).y.shape == (9, 0)
+    # method="fast" = the variant's fast path at its bench tolerance
+    T, P = golden["T"], golden["P"]
+    for sur, name, tol in ((s, "bs23", 1e-8), (soff, "dp54", 1e-7)):
+        a, b = sur.sweep(T, P, golden["L"], golden["U"], method="fast"), sur.sweep(T, P, golden["L"], golden["U"], method=name, rtol=tol, atol=tol)
+        assert torch.equal(a.y, b.y) and torch.equal(a.stats, b.stats)
 
 
 def test_status_reports_max_steps(surrogates, golden):
