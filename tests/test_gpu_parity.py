@@ -612,6 +612,35 @@ def test_full_size_sweep_properties(surrogates, model_sets, mech, variant, metho
     assert e.max() < 2e-4 and np.median(e) < 1e-5
 
 
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_configs_1_and_2_sampling_case_2D(surrogates, model_sets, conditions, variant):
+    """BASELINE configs 1 and 2: the 400 (T, P) rows of sampling_case_2D.csv with the full-length grid at L = 1.0 m,
+    u0 = 2.5 m/s (Eoff: LLNL_Eoff_wide_v2 as the script loads it, T = T0; Eon: temperature-profile MLP, outlet at the last
+    knot).  RODAS4 at 1e-9 within 1e-6 of the converged oracle solution on the GPU's own grids; the fast path at its bench
+    tolerance within 5e-5 (tolerance-level error), no stiff fallbacks."""
+    from oracle import c_oracle as CO
+    from oracle import reference_path as R
+    a = conditions["independent_2D"]
+    T, P = a[:, 0].astype(np.float32), (a[:, 1] * 1e5).astype(np.float32)
+    s = surrogates("LLNL", variant)
+    ms = model_sets("LLNL", variant)
+    res = s.sweep(T, P, rtol=1e-9, atol=1e-9, keep_grids=True).raise_on_failure()
+    tg = res.tgrid.cpu().numpy().T.copy()
+    if variant == "Eon":
+        assert int((res.idx_cut != 800).sum()) == 0
+        Tp = res.Tprof.cpu().numpy().T.copy()
+    else:
+        Tp = np.repeat(T[:, None], 801, 1)
+    idx = np.full(len(T), 800, np.int32)
+    truth, _ = CO.truth_batch(tg, Tp, R.inlet_concentration(T, P), ms.crnn.w_in, ms.crnn.w_b, ms.crnn.w_out, upto=idx, nthreads=8)
+    truth = np.clip(truth, 1e-6, 60.0)
+    assert np.max(rel_err(res.y.cpu().numpy().T, truth)) < 1e-6
+    fast = s.sweep(T, P, method="fast").raise_on_failure()
+    e = rel_err(fast.y.cpu().numpy().T, truth).max(1)
+    print(f"config {1 if variant == 'Eoff' else 2} ({variant}): fast path vs converged oracle: median {np.median(e):.2e} max {e.max():.2e}")
+    assert fast.stiff_fallbacks == 0 and e.max() < 5e-5
+
+
 def test_predict_n_ode_and_crnn_predict_seams(surrogates, golden):
     """Reference seam shapes: predict_n_ode -> [801, 9, n] on the MLP grid; crnn_predict -> [9, 801]."""
     s = surrogates("LLNL", "Eon")
