@@ -17,6 +17,7 @@
 // conditions, not millions; the arrays stay in L1).
 #pragma once
 #include "crnn_device.cuh"
+#include "fastmath.cuh"
 
 namespace pfr {
 
@@ -35,6 +36,7 @@ struct AdjointArgs {
     int substeps;
     double* loss;           // [n] per-condition MSE
     double* grad;           // [189][n] per-condition gradient
+    const FastTables* tables = nullptr;   // adjoint_warp_kernel: device copy of the log / exp tables (fastmath.cuh)
 };
 
 struct AdjNode {
@@ -218,6 +220,10 @@ template <bool kRamp>
 __global__ void __launch_bounds__(32 * ADJW_WARPS)
 adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointArgs a) {
     __shared__ AdjWarpScratch scratch[ADJW_WARPS];
+    __shared__ __align__(16) FastTables ft;   // table-driven log / exp (<= 2e-15 / 1 ulp): a third of libdevice's dependent chain
+    for (int e = threadIdx.x; e < LOGTAB_N; e += 32 * ADJW_WARPS) ft.logtab[e] = a.tables->logtab[e];
+    for (int e = threadIdx.x; e < EXPTAB_N; e += 32 * ADJW_WARPS) ft.exptab[e] = a.tables->exptab[e];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * ADJW_WARPS + warp;
     if (i >= a.n) return;  // warp-uniform
@@ -257,17 +263,16 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
     // node evaluation: forward quantities at (T, y) -> stored node `slot`; returns f_k, q_k, md_k, mz_k for this lane
     auto node = [&](int slot, double T, double y, double& f, double& q, double& md, double& mz) {
         const double Y = m_min(m_max(y, p.lb), p.ub);
-        double wvv = log(Y);
+        double wvv = fast_log(lane == NS + 1 ? T : Y, ft.logtab);   // lanes 0..8: ln Y_k; lane 10: ln T
         q = (y >= p.lb && y <= p.ub) ? 1.0 / Y : 0.0;
         if (lane == NS) wvv = -p.inv_R / T;
-        if (lane == NS + 1) wvv = log(T);
         if (lane < NS + 2) S.V[slot][lane] = wvv;
         if (lane == NS + 2) S.V[slot][11] = 1.0;
         __syncwarp();
         double z = lnA;
 #pragma unroll
         for (int r = 0; r < NS + 2; r++) z = fma(win_col[r], S.V[slot][r], z);
-        const double rr = exp(m_min(m_max(z, p.zlo), p.zhi));
+        const double rr = fast_exp(m_min(m_max(z, p.zlo), p.zhi), ft.exptab);
         mz = (z >= p.zlo && z <= p.zhi) ? 1.0 : 0.0;
         if (sp) S.R[slot][lane] = rr;
         __syncwarp();
@@ -303,17 +308,28 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
     double fb, qb, mdb, mzb;
     node(0, Tb, yb, fb, qb, mdb, mzb);
 
+    // the knot data of interval kk-1 (and the label of knot kk-1) are fetched one interval ahead of their use
+    float ta_n = a.tgrid[(size_t)(NTOT - 2) * n + i], Ta_n = kRamp ? a.Tprof[(size_t)(NTOT - 2) * n + i] : 0.f;
+    double ya_n = a.y_knots[((size_t)(NTOT - 2) * NS + k) * n + i];
+    float ref_n = lane < NOBS ? a.ref[((size_t)(NTOT - 1) * NOBS + lane) * n + i] : 0.f;
     for (int kk = NTOT - 1; kk >= 0; kk--) {
+        const float ref_c = ref_n;
+        if (kk > 0 && lane < NOBS) ref_n = a.ref[((size_t)(kk - 1) * NOBS + lane) * n + i];
         if (lane < NOBS) {
             const double pc = m_min(m_max(yb, p.lb), p.ub);
-            const double d = (pc - (double)a.ref[((size_t)kk * NOBS + lane) * n + i]) / sc;
+            const double d = (pc - (double)ref_c) / sc;
             loss = fma(d, d, loss);
             if (yb >= p.lb && yb <= p.ub) lam += 2.0 * d / sc * wnorm;
         }
         if (kk == 0) break;
-        const double ta = (double)a.tgrid[(size_t)(kk - 1) * n + i];
-        const double Ta = kRamp ? (double)a.Tprof[(size_t)(kk - 1) * n + i] : T0;
-        const double ya = a.y_knots[((size_t)(kk - 1) * NS + k) * n + i];
+        const double ta = (double)ta_n;
+        const double Ta = kRamp ? (double)Ta_n : T0;
+        const double ya = ya_n;
+        if (kk > 1) {
+            ta_n = a.tgrid[(size_t)(kk - 2) * n + i];
+            if (kRamp) Ta_n = a.Tprof[(size_t)(kk - 2) * n + i];
+            ya_n = a.y_knots[((size_t)(kk - 2) * NS + k) * n + i];
+        }
         double fa, qa, mda, mza;
         node(2, Ta, ya, fa, qa, mda, mza);  // lower end -> slot 2
         const double h = tb - ta, slope = (Tb - Ta) / h, hs = h / (double)a.substeps;

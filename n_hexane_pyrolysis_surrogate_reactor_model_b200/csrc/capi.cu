@@ -643,7 +643,11 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
                              double* grad, void* stream) {
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || n < 0 || substeps == 0) return PFR_EINVAL;
-    AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad};
+    {
+        const int rc = ensure_tables();
+        if (rc != PFR_OK) return rc;
+    }
+    AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad, g_tables};
     if (substeps > 0) {
         // one condition per warp
         const int blocks = (n + ADJW_WARPS - 1) / ADJW_WARPS;
