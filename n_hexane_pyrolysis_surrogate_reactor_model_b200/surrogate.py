@@ -270,16 +270,18 @@ class Surrogate:
         to the last knot.  Eon (...Eon_single_model.py:296-354): temperature MLP + full-length time MLP at
         (T,P,1.0,2.5) -> integrate; the outlet is the state at knot idx_cut = argmin|t_full - t_short[-1]|.
         method: an integrator name of `integrate`, or "fast" = the explicit fast path of this variant ("bs23" for Eon, "dp54" for
-        Eoff; stiff conditions fall back to the Rosenbrock kernel).  rtol / atol None: the method's default -- 1e-6 (the
-        reference's) for the Rosenbrock / dopri5 kernels, FAST_TOLERANCE for the fast paths (the setting at which their outlet
-        error is below RODAS4's at 1e-6).
+        Eoff; stiff conditions fall back to the Rosenbrock kernel).  rtol / atol None: 1e-6 (the reference's), except for
+        method="fast", which runs at FAST_TOLERANCE (the setting at which the fast path's outlet error is below RODAS4's at
+        1e-6).
         integrator_events: a list that receives one (start, end) pair of CUDA events recorded around the integrator launch
         (bench.py times the dominant kernel inside the timed steps with it).
         """
+        default_tol = 1.0e-6
         if method == "fast":
             method = "bs23" if self.energy_on else "dp54"
-        rtol = FAST_TOLERANCE.get(method, 1e-6) if rtol is None else rtol
-        atol = FAST_TOLERANCE.get(method, 1e-6) if atol is None else atol
+            default_tol = FAST_TOLERANCE[method]
+        rtol = default_tol if rtol is None else rtol
+        atol = default_tol if atol is None else atol
         def timed_integrate(*a, **k):
             if integrator_events is None:
                 return self.integrate(*a, **k)
