@@ -33,7 +33,7 @@ def test_argument_validation_without_a_device():
     from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
     L = _lib.lib()
     assert L.pfr_mlp_workspace_bytes(1000, 0) == (4 * 512 + 800) * 1024 * 4
-    assert L.pfr_mlp_workspace_bytes(10 ** 6, 0) == (4 * 512 + 800) * 65536 * 4
+    assert L.pfr_mlp_workspace_bytes(10 ** 6, 0) == (4 * 512 + 800) * (2 * 4 * 148 * 128) * 4   # default chunk: two lanes of 592 row tiles
     assert L.pfr_integrate(None, 0, 64, 4, None, None, None, None, None, None, None, 1e-6, 1e-6, 0, 0, None, None, None, None, None) == -1
     assert L.pfr_integrate(None, 0, 64, 0, None, None, None, None, None, None, None, 1e-6, 1e-6, 0, 0, None, None, None, None, None) == 0
     assert L.pfr_rhs(None, 3, None, None, None, 16, None) == -1
