@@ -94,10 +94,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Round to TF32 (10 explicit mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 returns for every finite
+// input, as two integer instructions: the PTX conversion expands to ~3.2 SASS instructions with its NaN handling (FSETP / SEL),
+// and the hidden-layer epilogue, which is bound by instruction issue, performs 256 of them per thread and tile.  (Infinity
+// stays infinity, the largest finite values round up to it, a NaN stays a NaN with some payload bits cleared.)
 __device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 struct GemmArgs {
