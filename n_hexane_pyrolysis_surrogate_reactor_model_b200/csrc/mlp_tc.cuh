@@ -94,6 +94,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// packed float32 pairs (sm_100: add.rn.f32x2 adds two IEEE float32 lanes with one instruction)
+__device__ __forceinline__ uint64_t pack2(uint32_t a, uint32_t b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // Round to TF32 (10 explicit mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 returns for every finite
 // input, as two integer instructions: the PTX conversion expands to ~3.2 SASS instructions with its NaN handling (FSETP / SEL),
 // and the hidden-layer epilogue, which is bound by instruction issue, performs 256 of them per thread and tile.  (Infinity
@@ -271,18 +289,28 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                 const int o0 = n0 + c * EPI_COLS;
                 float x[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    // float32 round-to-nearest sum of the three K-thirds, then the cross terms, then the bias
-                    const float main = (__uint_as_float(w[1][j]) + __uint_as_float(w[2][j])) + __uint_as_float(w[3][j]);
-                    x[j] = (main + __uint_as_float(w[0][j])) + bias_s[c * EPI_COLS + j];
+                for (int j = 0; j < 16; j += 2) {
+                    // float32 round-to-nearest sum of the three K-thirds, then the cross terms, then the bias -- two columns per
+                    // instruction (add.rn.f32x2: the epilogue is bound by instruction issue)
+                    const uint64_t main = add_f32x2(add_f32x2(pack2(w[1][j], w[1][j + 1]), pack2(w[2][j], w[2][j + 1])), pack2(w[3][j], w[3][j + 1]));
+                    const float2 bb = *reinterpret_cast<const float2*>(&bias_s[c * EPI_COLS + j]);
+                    const uint64_t xx = add_f32x2(add_f32x2(main, pack2(w[0][j], w[0][j + 1])), pack2(__float_as_uint(bb.x), __float_as_uint(bb.y)));
+                    uint32_t x0, x1;
+                    unpack2(xx, x0, x1);
+                    x[j] = __uint_as_float(x0);
+                    x[j + 1] = __uint_as_float(x1);
                 }
                 if (!kFinal) {
                     float hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float r = fmaxf(x[j], 0.f);
-                        hi[j] = rn_tf32(r);
-                        lo[j] = rn_tf32(r - hi[j]);
+                    for (int j = 0; j < 16; j += 2) {
+                        const float r0 = fmaxf(x[j], 0.f), r1 = fmaxf(x[j + 1], 0.f);
+                        hi[j] = rn_tf32(r0);
+                        hi[j + 1] = rn_tf32(r1);
+                        uint32_t d0, d1;
+                        unpack2(sub_f32x2(pack2(__float_as_uint(r0), __float_as_uint(r1)), pack2(__float_as_uint(hi[j]), __float_as_uint(hi[j + 1]))), d0, d1);
+                        lo[j] = rn_tf32(__uint_as_float(d0));
+                        lo[j + 1] = rn_tf32(__uint_as_float(d1));
                     }
                     // transpose through this warp's slab: lane = row on the way in (16-byte chunks XOR-swizzled by the
                     // row so that neither side has bank conflicts), 4 lanes per row on the way out
