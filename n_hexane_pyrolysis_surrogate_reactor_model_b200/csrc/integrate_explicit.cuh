@@ -411,7 +411,10 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
 #ifndef PFR_DP54_KINK
 #define PFR_DP54_KINK 1000   // as PFR_BS23_KINK; free steps are long, the margin matters more: at 1e-7 the p99 error falls 500x
 #endif
-constexpr int DP54_BLOCK = 128, DP54_CTAS_PER_SM = 2, DP54_STAGES = 7, DP54_MAX_ATTEMPTS = 2000;
+#ifndef PFR_DP54_MINB
+#define PFR_DP54_MINB 3   // CTAs per SM: 168 registers, no spills (the slopes live in shared memory), 12 warps / SM; 2 CTAs: 11 % slower
+#endif
+constexpr int DP54_BLOCK = 128, DP54_CTAS_PER_SM = PFR_DP54_MINB, DP54_STAGES = 7, DP54_MAX_ATTEMPTS = 2000;
 template <typename real> constexpr size_t dp54_smem_bytes() { return (size_t)DP54_STAGES * NS * DP54_BLOCK * sizeof(real); }
 
 struct Dp54Tableau {
