@@ -562,8 +562,8 @@ static int dispatch_bs23(const CrnnParams<real>& p, const RodasArgs& a0, cudaStr
     CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
     const int full = (a.n + BS23_BLOCK - 1) / BS23_BLOCK, persistent = BS23_CTAS_PER_SM * g_num_sms;
     const int grid = full < persistent ? full : persistent;
-    if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, 0, st>>>(p, a);
-    else bs23_kernel<real, false><<<grid, BS23_BLOCK, 0, st>>>(p, a);
+    if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
+    else bs23_kernel<real, false><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
     CK_LAUNCH("bs23_kernel");
     return PFR_OK;
 }

@@ -32,6 +32,12 @@
 
 namespace pfr {
 
+#ifndef PFR_BS23_SMEM_STATE
+#define PFR_BS23_SMEM_STATE 1   // FSAL slope and the two running combinations of a step in shared memory (27 KB per CTA) instead of
+                                // registers: 252 -> 168 registers without spills, i.e. three CTAs per SM; measured 84.5 -> 78.4 ms
+                                // for 2^20 conditions at 1e-8 (with two CTAs the shared-memory version is 4 % slower than registers)
+#endif
+template <typename real> constexpr size_t bs23_smem_bytes() { return PFR_BS23_SMEM_STATE ? (size_t)3 * NS * 128 * sizeof(real) : 0; }
 #ifndef PFR_BS23_KINK
 #define PFR_BS23_KINK 0     // error margin demanded of a step that straddles the kink of the lower state clamp; 0 = off.
                             // Measured with 100 (2^20 LHS conditions, 1e-8): median outlet error 2.1e-7 -> 6.1e-8, p99 3.2e-6 ->
@@ -40,9 +46,9 @@ namespace pfr {
 #endif
 constexpr int BS23_BLOCK = 128;
 #ifndef PFR_BS23_MINB
-#define PFR_BS23_MINB 2   // CTAs per SM.  2: 250 registers, no spills, 8 warps / SM; 3 (168 registers, 94 B of spills): 30 % slower
+#define PFR_BS23_MINB (PFR_BS23_SMEM_STATE ? 3 : 2)   // CTAs per SM: 168 registers / 12 warps with the shared-memory state, else 252 / 8
 #endif
-constexpr int BS23_CTAS_PER_SM = PFR_BS23_MINB;   // persistent grid: 250 registers x 128 threads, two CTAs fill the register file
+constexpr int BS23_CTAS_PER_SM = PFR_BS23_MINB;   // persistent grid: as many CTAs as fit
 constexpr int PFR_ST_STIFF_ = 4;
 
 template <typename real> __device__ __forceinline__ real t_log(real x, const FastTables& ft);
@@ -214,9 +220,23 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     double t = 0.0, t_final = 0.0, tk = 0.0, tk1 = 0.0, hprop = 0.0;
     real Tk = real(0), Tk1 = real(0), slope = real(0);
     float t_ahead = 0.f, T_ahead = 0.f;
-    real y[NS], k1[NS];
+    real y[NS];
+#if PFR_BS23_SMEM_STATE
+    // FSAL slope and the two running combinations of a step live in shared memory ([vector][species][thread], conflict-free):
+    // 54 registers fewer, which is what lets a third CTA onto the SM
+    extern __shared__ __align__(16) unsigned char bs_dyn[];
+    real* const stv = reinterpret_cast<real*>(bs_dyn) + threadIdx.x;
+#define K1(k) stv[(0 * NS + (k)) * BS23_BLOCK]
+#define ACC(k) stv[(1 * NS + (k)) * BS23_BLOCK]
+#define ER(k) stv[(2 * NS + (k)) * BS23_BLOCK]
+#else
+    real k1[NS], acc[NS], er[NS];
+#define K1(k) k1[k]
+#define ACC(k) acc[k]
+#define ER(k) er[k]
+#endif
 #pragma unroll
-    for (int k = 0; k < NS; k++) { y[k] = real(0); k1[k] = real(0); }
+    for (int k = 0; k < NS; k++) { y[k] = real(0); K1(k) = real(0); }
 
     while (true) {
         const unsigned want = __ballot_sync(0xffffffffu, !have && !exhausted);
@@ -233,7 +253,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                     i = a.perm ? a.perm[slot] : slot;
                     kend = a.idx_end ? a.idx_end[i] : NTOT - 1;
 #pragma unroll
-                    for (int k = 0; k < NS; k++) { y[k] = real(0); k1[k] = real(0); }   // (k1 is multiplied by h = 0 in the entry step)
+                    for (int k = 0; k < NS; k++) { y[k] = real(0); K1(k) = real(0); }   // (k1 is multiplied by h = 0 in the entry step)
                     y[NS - 3] = real(a.c0[i]);
                     t = (double)a.tgrid[i];
                     t_final = (double)a.tgrid[(size_t)kend * n + i];
@@ -276,9 +296,9 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             // inlined copies made the loop body ~59 KB and instruction fetch the largest stall, 22 % of all stall cycles).
             // The stage index is warp-uniform.  acc / er accumulate the solution and error combinations as the slopes arrive:
             //   y1 = y + h (2/9 k1 + 1/3 k2 + 4/9 k3),   err = h (-5/72 k1 + 1/12 k2 + 1/9 k3 - 1/8 k4)
-            real k2[NS], w[NS], acc[NS], er[NS];
+            real k2[NS], w[NS];
 #pragma unroll
-            for (int k = 0; k < NS; k++) w[k] = fma(real(0.5) * h, k1[k], y[k]);
+            for (int k = 0; k < NS; k++) w[k] = fma(real(0.5) * h, K1(k), y[k]);
 #pragma unroll 1
             for (int stage = 0; stage < 3; stage++) {
                 const real cs = stage == 0 ? real(0.5) : (stage == 1 ? real(0.75) : real(1));
@@ -287,15 +307,16 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 if (stage == 0) {
 #pragma unroll
                     for (int k = 0; k < NS; k++) {
-                        acc[k] = fma(real(1.0 / 3.0), k2[k], real(2.0 / 9.0) * k1[k]);
-                        er[k] = fma(real(1.0 / 12.0), k2[k], real(-5.0 / 72.0) * k1[k]);
+                        const real k1k = K1(k);
+                        ACC(k) = fma(real(1.0 / 3.0), k2[k], real(2.0 / 9.0) * k1k);
+                        ER(k) = fma(real(1.0 / 12.0), k2[k], real(-5.0 / 72.0) * k1k);
                         w[k] = fma(real(0.75) * h, k2[k], y[k]);
                     }
                 } else if (stage == 1) {
 #pragma unroll
                     for (int k = 0; k < NS; k++) {
-                        w[k] = fma(h, fma(real(4.0 / 9.0), k2[k], acc[k]), y[k]);   // third-order solution y1
-                        er[k] = fma(real(1.0 / 9.0), k2[k], er[k]);
+                        w[k] = fma(h, fma(real(4.0 / 9.0), k2[k], ACC(k)), y[k]);   // third-order solution y1
+                        ER(k) = fma(real(1.0 / 9.0), k2[k], ER(k));
                     }
                 }
             }   // k2 now holds k4 = f(t + h, y1): the next step's k1
@@ -304,7 +325,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             bool finite = true;
 #pragma unroll
             for (int k = 0; k < NS; k++) {
-                const real ek = h * fma(real(-1.0 / 8.0), k2[k], er[k]);
+                const real ek = h * fma(real(-1.0 / 8.0), k2[k], ER(k));
                 const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
                 e2 = fma(ek * isk, ek * isk, e2);
                 d0 = fma(y[k] * isk, y[k] * isk, d0);     // only used by a fresh condition (first-step guess)
@@ -327,7 +348,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             if (fresh) {
                 // the zero-length step left y unchanged and k2 = f(t0, y0); Hairer-style first step from |y0| and |f0|
 #pragma unroll
-                for (int k = 0; k < NS; k++) k1[k] = k2[k];
+                for (int k = 0; k < NS; k++) K1(k) = k2[k];
                 d0 = m_sqrt<real>(d0 / real(NS));
                 d1 = m_sqrt<real>(d1 / real(NS));
                 const double h0 = (d0 < real(1e-5) || d1 < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
@@ -338,7 +359,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 hprop = clip ? fmax(hprop, hs * f) : hs * f;
                 nacc++;
 #pragma unroll
-                for (int k = 0; k < NS; k++) { y[k] = w[k]; k1[k] = k2[k]; }
+                for (int k = 0; k < NS; k++) { y[k] = w[k]; K1(k) = k2[k]; }
                 if (clip) {
                     t = tk1;
                     kc++;
@@ -395,6 +416,9 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
         }
     }
 }
+#undef K1
+#undef ACC
+#undef ER
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Free-stepping explicit integrator for the ISOTHERMAL sweep (Eoff: T = T0, integrate to t_end, no knots): Dormand-Prince 5(4)
