@@ -276,7 +276,7 @@ def run_ours(args, emit=print):
         sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, f"{mech}.npz"), variant), device=dev)
         tol2 = tols.get(method, args.rtol)
         kw2 = dict(method=method, precision=prec, rtol=tol2, atol=tol2 if method in tols else args.atol)
-        ms, res, _ = time_steps(lambda: gather_outlets(sur.sweep(T, P, L, U, **kw2).y, n_total), 2, 1)
+        ms, res, _ = time_steps(lambda: gather_outlets(sur.sweep(T, P, L, U, **kw2).y, n_total), 2, 3)   # 3 warm-ups: allocator steady state
         r = sur.sweep(T, P, L, U, **kw2)
         name = f"{mech}_{variant}" + ("" if prec == 64 else f"_{method}_f{prec}")
         variants[name] = {"value": n_total * 2 / (ms * 1e-3), "ms_per_step": ms / 2, "failed_trajectories": int((r.status != 0).sum().item()),
@@ -316,7 +316,7 @@ def run_ours(args, emit=print):
                      "peak_source": "pfr_measure_peaks(): dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
                      "kernel_ms": result["kms"], "kernel_ms_source": "CUDA events around the kernel launch inside the timed steps (mean over the steps)",
                      "kernel_share_of_step": e["integrator_share_of_step"],
-                     "traffic": 76.5e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01g_ncu_full_bs23_fp64.txt: 76.5 KB per condition x n "
+                     "traffic": 74.8e3 * n, "traffic_source": "dram__bytes_read+write of this kernel in profiles/r01h_ncu_full_bs23_fp64.txt: 74.8 KB per condition x n "
                                                                 "(the two [801][n] float32 grids are gathered through the cost-sort permutation: one 32-byte sector per 4-byte knot value)",
                      "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
                                    f"BS23 step overhead {FP64_STEP_BS23} (stage sums, error norm; ROS3: {FP64_STEP_ROS3}, RODAS4: {FP64_STEP}); see DESIGN.md"},
