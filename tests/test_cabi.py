@@ -38,6 +38,17 @@ def test_argument_validation_without_a_device():
     assert L.pfr_integrate(None, 0, 64, 0, None, None, None, None, None, None, None, 1e-6, 1e-6, 0, 0, None, None, None, None, None) == 0
     assert L.pfr_rhs(None, 3, None, None, None, 16, None) == -1
     assert L.pfr_measure_peaks(None) == -1
+    # the predictor-MLP trainer and the fast-path integrators validate before touching CUDA as well
+    import ctypes
+    h = ctypes.c_void_p()
+    assert L.pfr_mlp_trainer_create(3, None, None, ctypes.byref(h)) == -1          # in_dim must be 2 or 4
+    assert L.pfr_mlp_trainer_create(2, None, None, None) == -1
+    assert L.pfr_mlp_trainer_step(None, None, None, 32, 1e-3, 0.9, 0.999, 1e-8, None, None) == -1
+    assert L.pfr_mlp_trainer_forward(None, None, 0, None, None) == 0                # empty batch: no-op
+    assert L.pfr_mlp_trainer_destroy(None) == 0
+    assert L.pfr_integrate(None, 7, 64, 4, None, None, None, None, None, None, None, 1e-6, 1e-6, 0, 0, None, None, None, None, None) == -1
+    assert L.pfr_time_grid(None, None, None, None, None, 0, None, None, 0, None, 0, 0, None) == 0     # empty batch
+    assert L.pfr_temp_profile(None, None, None, 0, None, 0, None, 0, 0, None) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch):
