@@ -155,6 +155,12 @@ class MlpTrainer:
         return MLPParams(w, b, float(output_scale[0]), float(output_scale[1]))
 
 
+def step_lr(settings: MlpTrainSettings, epoch: int) -> float:
+    """Learning rate in force during epoch `epoch` (0-based) under lr_scheduler.StepLR(step_size, gamma) stepped once per epoch
+    after the training batches (…2D.py:128,162; …4D.py:165,192)."""
+    return settings.learning_rate * settings.lr_gamma ** (epoch // settings.lr_step_size)
+
+
 def epoch_batches(n: int, batch_size: int, generator: torch.Generator):
     """DataLoader(shuffle=True, drop_last=False): a fresh permutation per epoch, consecutive slices of batch_size."""
     perm = torch.randperm(n, generator=generator)
@@ -178,13 +184,11 @@ def train(dataset: MlpDataset, settings: MlpTrainSettings, weights=None, biases=
     nb_valid = (xv.shape[0] + settings.batch_size - 1) // settings.batch_size
     losses = torch.zeros(nb_train + nb_valid, dtype=torch.float32, device=dev)
     hist_t, hist_v = [], []
-    lr = settings.learning_rate
     for epoch in range(settings.num_epochs if num_epochs is None else num_epochs):
+        lr = step_lr(settings, epoch)
         for j, idx in enumerate(epoch_batches(xt.shape[0], settings.batch_size, g)):
             idx = idx.to(dev)
             tr.step(xt[idx].contiguous(), yt[idx].contiguous(), lr, losses[j])
-        if (epoch + 1) % settings.lr_step_size == 0:     # scheduler.step() after the training batches of the epoch
-            lr *= settings.lr_gamma
         for j, idx in enumerate(epoch_batches(xv.shape[0], settings.batch_size, g)):
             idx = idx.to(dev)
             tr.loss(xv[idx].contiguous(), yv[idx].contiguous(), losses[nb_train + j])

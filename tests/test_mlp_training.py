@@ -42,6 +42,19 @@ def test_dataset_split_and_scaling(model_sets, conditions):
     assert np.allclose(xt[:, 0], ((a[tr, 0] - 870.0) / 280.0).astype(np.float32))
 
 
+def test_step_lr_matches_torch_scheduler():
+    """The host-side learning-rate schedule equals torch.optim.lr_scheduler.StepLR(100, 0.6) stepped once per epoch."""
+    from torch.optim import lr_scheduler
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.mlp_training import TIME_4D_SETTINGS, step_lr
+    par = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([par], lr=TIME_4D_SETTINGS.learning_rate)
+    sched = lr_scheduler.StepLR(opt, step_size=100, gamma=0.6)
+    for epoch in range(450):
+        assert abs(step_lr(TIME_4D_SETTINGS, epoch) - opt.param_groups[0]["lr"]) < 1e-15
+        opt.step()
+        sched.step()
+
+
 def test_oracle_training_reduces_loss(model_sets, conditions):
     """The oracle itself (reference operators on the CPU): a few epochs on teacher labels bring the loss down."""
     from n_hexane_pyrolysis_surrogate_reactor_model_b200.mlp_training import TEMP_2D_SETTINGS, epoch_batches, initial_parameters
