@@ -114,7 +114,11 @@ int pfr_rhs(crnn_model_t m, int n, const void* T, const void* u, void* du, int p
  * (requires tgrid); status[n]; stats[3][n] = accepted steps, rejected steps, RHS evaluations (or NULL).
  * perm[n] or NULL: thread j integrates condition perm[j] -- a cost-sorted order keeps the lanes of a warp in
  * step with each other; every array is still indexed by the condition, so outputs need no un-permuting.
- * flags: PFR_FLAG_DENSE_RAW leaves y_dense unclamped (the training step needs the raw knot states). */
+ * flags: PFR_FLAG_DENSE_RAW leaves y_dense unclamped (the training step needs the raw knot states).
+ * method: PFR_METHOD_* above.  The explicit fast paths (BS23: tgrid required; DP54: t_end only, no Tprof / idx_end / y_dense)
+ * stop a condition that turns out stiff with status PFR_ST_STIFF; the caller integrates those conditions again with
+ * PFR_METHOD_ROS3 / PFR_METHOD_RODAS4 (the host mirror does: Surrogate.integrate, stiff_fallback).  stats of BS23 count one
+ * zero-length entry step per condition: rhs = 3 (attempts + 1); DP54: rhs = 6 attempts + 1. */
 int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
                   double rtol, double atol, int max_steps, int flags, void* y_out, void* y_dense, int* status,
