@@ -411,10 +411,13 @@ def cpu_baseline(args, variant="Eon", sample=None):
     t0 = time.time()
     y = D.sweep_parallel(ms, T[idx], P[idx], L[idx], U[idx], cores)
     dt = time.time() - t0
-    out = {"value": sample / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
+    failed = int(np.isnan(y).any(axis=1).sum())
+    # trajectories the port COMPLETED per second: a condition on which torchdiffeq's asserts would fire (`underflow in dt`; the
+    # reference script aborts there) is attempted, counted under "failed" and not counted as work done
+    out = {"value": (sample - failed) / dt, "unit": "trajectories/s", "cores": cores, "kind": "port", "attempted": sample,
            "sample": f"{sample} of the {len(T)} LHS conditions (every {len(T) // sample}-th), LLNL {variant}, oracle/reference_driver.py "
                      f"(torch CPU float32 ops, dopri5 1e-6/1e-6, 801 outputs, per-condition loop) over {cores} processes",
-           "seconds": dt, "failed": int(np.isnan(y).any(axis=1).sum())}
+           "seconds": dt, "failed": failed}
     # for context: the same algorithm as compiled C (oracle/crnn_oracle.c), ODE part only, all cores
     m = min(len(T), 8192)
     sel = np.arange(0, len(T), len(T) // m)[:m]

@@ -239,6 +239,56 @@ class SolveStats:
     rejected: int = 0
 
 
+def select_initial_step(f, t0, y0, f0, rtol, atol):
+    """torchdiffeq `_impl/misc.py::_select_initial_step(func, t0, y0, order=4, rtol, atol, norm=rms, f0)` (Hairer, Norsett &
+    Wanner I, II.4): returns dt as a float64 tensor.  `f(t, y)` is the counted right-hand side of odeint_dopri5."""
+    sd = y0.dtype
+    with torch.no_grad():
+        scale = atol + torch.abs(y0) * rtol
+        d0 = _rms(y0 / scale)
+        d1 = _rms(f0 / scale)
+        if d0 < 1e-5 or d1 < 1e-5:
+            h0 = torch.tensor(1e-6, dtype=sd)
+        else:
+            h0 = 0.01 * d0 / d1
+        h0 = h0.abs()
+        y1 = y0 + h0 * f0
+        f1 = f(t0 + h0, y1)
+        d2 = torch.abs(_rms((f1 - f0) / scale) / h0)
+        if d1 <= 1e-15 and d2 <= 1e-15:
+            h1 = torch.max(torch.tensor(1e-6, dtype=sd), h0 * 1e-3)
+        else:
+            h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+        h1 = h1.abs()
+        return torch.min(100 * h0, h1).to(torch.float64)
+
+
+def rk_step(f, ya, fa, ta, dt, alpha, beta, c_err):
+    """torchdiffeq `_impl/rk_common.py::_runge_kutta_step` for the dopri5 tableau: (y1, f1, y1_error, k[9, 7])."""
+    sd = ya.dtype
+    tb = ta + dt
+    t0s, dts, t1s = ta.to(sd), dt.to(sd), tb.to(sd)
+    # k is kept as a list of stage derivatives and stacked for the weighted sums: the same arithmetic as
+    # torchdiffeq's pre-allocated k[..., i] buffer, but differentiable (no in-place writes into saved tensors)
+    ks = [fa]
+    for al, be in zip(alpha, beta):
+        if float(al) == 1.0:
+            ti, prev = t1s, True
+        else:
+            ti, prev = t0s + al * dts, False
+        kj = torch.stack(ks, dim=-1)
+        yi = ya + torch.sum(kj * (be * dts), dim=-1).view_as(fa)
+        ks.append(f(ti, yi, prev))
+    k = torch.stack(ks, dim=-1)
+    return yi, k[..., -1], torch.sum(k * (dts * c_err), dim=-1), k
+
+
+def dopri5_tableau(dtype=torch.float64):
+    """(alpha, beta rows, c_sol, c_err) of torchdiffeq `_impl/dopri5.py` as tensors of `dtype`."""
+    return ([torch.tensor(a, dtype=dtype) for a in _ALPHA], [torch.tensor(b, dtype=dtype) for b in _BETA],
+            torch.tensor(_C_SOL, dtype=dtype), torch.tensor(_C_ERR, dtype=dtype))
+
+
 def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6, stats: SolveStats | None = None,
                   max_num_steps=2 ** 31 - 1):
     """torchdiffeq.odeint(func, y0, t, method='dopri5') restated (see module header).  Returns [len(t), 9]."""
@@ -262,24 +312,7 @@ def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6,
     # _before_integrate + _select_initial_step(order = 5 - 1); torchdiffeq decorates _select_initial_step,
     # _compute_error_ratio and _optimal_step_size with @torch.no_grad(): step sizes carry no gradient
     f0 = f(t[0], y0)
-    with torch.no_grad():
-        scale = atol + torch.abs(y0) * rtol
-        d0 = _rms(y0 / scale)
-        d1 = _rms(f0 / scale)
-        if d0 < 1e-5 or d1 < 1e-5:
-            h0 = torch.tensor(1e-6, dtype=sd)
-        else:
-            h0 = 0.01 * d0 / d1
-        h0 = h0.abs()
-        y1 = y0 + h0 * f0
-        f1 = f(t[0] + h0, y1)
-        d2 = torch.abs(_rms((f1 - f0) / scale) / h0)
-        if d1 <= 1e-15 and d2 <= 1e-15:
-            h1 = torch.max(torch.tensor(1e-6, dtype=sd), h0 * 1e-3)
-        else:
-            h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
-        h1 = h1.abs()
-        dt = torch.min(100 * h0, h1).to(torch.float64)
+    dt = select_initial_step(f, t[0], y0, f0, rtol, atol)
 
     rk_y, rk_f, rk_t0, rk_t1 = y0, f0, t[0], t[0]
     interp = [y0] * 5
@@ -294,23 +327,7 @@ def odeint_dopri5(func, y0: torch.Tensor, t: torch.Tensor, rtol=1e-6, atol=1e-6,
             tb = ta + dt
             assert ta + dt > ta, "underflow in dt"
             assert torch.isfinite(ya).all(), "non-finite values in state `y`"
-            # ---- _runge_kutta_step ----
-            t0s, dts, t1s = ta.to(sd), dt.to(sd), tb.to(sd)
-            # k is kept as a list of stage derivatives and stacked for the weighted sums: the same arithmetic as
-            # torchdiffeq's pre-allocated k[..., i] buffer, but differentiable (no in-place writes into saved tensors)
-            ks = [fa]
-            for j, (al, be) in enumerate(zip(alpha, beta)):
-                if float(al) == 1.0:
-                    ti, prev = t1s, True
-                else:
-                    ti, prev = t0s + al * dts, False
-                kj = torch.stack(ks, dim=-1)
-                yi = ya + torch.sum(kj * (be * dts), dim=-1).view_as(fa)
-                ks.append(f(ti, yi, prev))
-            k = torch.stack(ks, dim=-1)
-            yb = yi
-            fb = k[..., -1]
-            err = torch.sum(k * (dts * c_err), dim=-1)
+            yb, fb, err, k = rk_step(f, ya, fa, ta, dt, alpha, beta, c_err)
             with torch.no_grad():
                 tol = atol + rtol * torch.max(ya.abs(), yb.abs())
                 ratio = _rms(err / tol).abs()
