@@ -8,7 +8,9 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
  *   - per-condition arrays are SoA with the condition index fastest: x[n], grid[801][n], y[9][n];
  *   - return value: PFR_OK or a negative PFR_E* code; per-condition solver outcomes go to status[n].
- * One host thread per GPU; handles are bound to the device current at creation.
+ * One host thread per GPU.  Library state is kept per device (tables, work-queue counters, auxiliary streams); handles that own
+ * device memory (pfr_mlp_t, pfr_mlp_trainer_t, pfr_sweep_t) are bound to the device current at creation, and a call that arrives
+ * with another device current returns PFR_EINVAL.  A crnn_model_t holds host memory only and may be used on any device.
  */
 #ifndef CRNN_PFR_H
 #define CRNN_PFR_H
@@ -53,6 +55,7 @@ extern "C" {
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;
 typedef struct pfr_mlp_trainer* pfr_mlp_trainer_t;
+typedef struct pfr_sweep* pfr_sweep_t;
 
 int pfr_version(void);
 const char* pfr_status_string(int code);
@@ -67,6 +70,10 @@ unsigned long long pfr_launch_count(void);
  *   (...Eoff_single_model.py:123-129; the WIDE trainer uses zlo/zhi = -/+10). */
 int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out);
 int crnn_model_destroy(crnn_model_t m);
+/* New parameters for an existing handle (the training loop: one call per optimisation step, ParameterConverter(p) of
+ * SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py:194-228 evaluated on the host).  Parameters reach the kernels by
+ * value at launch time: launches already enqueued keep the old ones, later launches see the new ones; clamps are unchanged. */
+int crnn_model_update(crnn_model_t m, const float* w_in, const float* w_b, const float* w_out);
 
 /* 512-wide predictor MLP (nn.Linear layout [out][in], HOST pointers) + its .pkl output scaler
  *   MultiLayerPerceptron_time / MLP_Time / MLP_Temp   ...Eoff_single_model.py:192-208, ...Eon_single_model.py:94-128
@@ -123,6 +130,36 @@ int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float*
                   const float* tgrid, const float* Tprof, const float* t_end, const int* idx_end, const int* perm,
                   double rtol, double atol, int max_steps, int flags, void* y_out, void* y_dense, int* status,
                   int* stats, void* stream);
+
+/* ---- the whole sweep as one call ----------------------------------------------------------------------------------------
+ * main() of SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:259-369 (temp_mlp NULL: isothermal sweep, T = T0, outlet at the
+ * last knot of the (T, P, L, u0) time grid) and of ...Eon_single_model.py:279-354 (coupled sweep: temperature profile and
+ * full-length grid at (T, P, 1.0 m, 2.5 m/s), outlet = state at knot idx_cut = argmin |t_full - t_short[-1]|; L = u0 = NULL:
+ * the outlet is the last knot of the full-length grid, as for sampling_case_2D.csv).
+ * The handle owns every intermediate buffer for up to n_max conditions (pfr_sweep_device_bytes): inputs in visiting order,
+ * c0, the two [801][n] grids, outlet knots / times, three MLP workspaces, two side streams for the independent MLP passes.
+ * pfr_sweep_run is asynchronous on `stream` and never waits for the host:
+ *   visiting order (counting sort by a cost proxy known before the MLPs run: L / u0 resp. T0, expensive first; the grids are
+ *   then WRITTEN in the order the integrator reads them) -> pfr_inlet_concentration -> pfr_temp_profile / pfr_time_grid x2 ->
+ *   pfr_idx_cut -> integrator -> Rosenbrock fallback over the device-side list of conditions the explicit fast path flagged
+ *   stiff -> results scattered to the caller's order.
+ * T, P, L, u0 [n], y_out [9][n] (precision 64: double, 32: float), status [n], stats [3][n] or NULL (a condition that went
+ * through the fallback reports the fallback's counters), idx_cut_out [n] / t_end_out [n] or NULL -- all in the caller's order;
+ * stiff_count_out: one int on the device or NULL.
+ * method: coupled PFR_METHOD_BS23 | ROS3 | RODAS4; isothermal PFR_METHOD_DP54 | ROS3 | RODAS4. */
+#define PFR_SWEEP_NO_ORDER 1     /* flags: visit the conditions in the caller's order */
+#define PFR_SWEEP_NO_FALLBACK 2  /* flags: leave conditions flagged PFR_ST_STIFF as they are */
+int pfr_sweep_create(crnn_model_t crnn, pfr_mlp_t time_mlp, pfr_mlp_t temp_mlp, int n_max, pfr_sweep_t* out);
+int pfr_sweep_destroy(pfr_sweep_t s);
+size_t pfr_sweep_device_bytes(int n_max, int energy_on);
+int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, const float* L, const float* u0, int n, int method, int precision,
+                  double rtol, double atol, int max_steps, int flags, void* y_out, int* status, int* stats, int* idx_cut_out,
+                  float* t_end_out, int* stiff_count_out, void* stream);
+/* conditions the last run handed to the Rosenbrock fallback: written to stiff_count_out (one int on the device, caller-owned) if
+ * given, else kept by the handle and read with this call (which synchronises the device) */
+int pfr_sweep_stiff_count(pfr_sweep_t s, int* count);
+/* device time of the last run's integrator launch, between two events of the handle (waits for that launch to finish) */
+int pfr_sweep_integrator_ms(pfr_sweep_t s, float* ms);
 
 /* Loss and gradient of one training step for a batch of conditions
  *   loss = Trainer.loss_n_ode(p, i_exp); loss.backward()   SURROGATE_MODEL_TRAINING/WIDE_Eoff_surrogate_model_training.py:387-396,414-416

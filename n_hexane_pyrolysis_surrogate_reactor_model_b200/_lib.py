@@ -16,6 +16,7 @@ METHOD_ROS3 = 3
 METHOD_BS23 = 4
 METHOD_DP54 = 5
 ST_STIFF = 4
+SWEEP_NO_ORDER, SWEEP_NO_FALLBACK = 1, 2
 STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow",
                4: "stiff for the explicit fast path (integrate with ros3 / rodas4)"}
 
@@ -38,6 +39,18 @@ def _declare(lib):
     lib.pfr_launch_count.restype = ctypes.c_ulonglong
     lib.crnn_model_create.argtypes = [c_float_p, c_float_p, c_float_p, c_double_p, ctypes.POINTER(c_void_p)]
     lib.crnn_model_destroy.argtypes = [c_void_p]
+    lib.crnn_model_update.argtypes = [c_void_p, c_float_p, c_float_p, c_float_p]
+    lib.crnn_model_update.restype = c_int
+    lib.pfr_sweep_create.argtypes = [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p)]
+    lib.pfr_sweep_destroy.argtypes = [c_void_p]
+    lib.pfr_sweep_device_bytes.argtypes = [c_int, c_int]
+    lib.pfr_sweep_device_bytes.restype = c_size_t
+    lib.pfr_sweep_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pfr_sweep_stiff_count.argtypes = [c_void_p, ctypes.POINTER(c_int)]
+    lib.pfr_sweep_integrator_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+    for name in ("pfr_sweep_create", "pfr_sweep_destroy", "pfr_sweep_run", "pfr_sweep_stiff_count", "pfr_sweep_integrator_ms"):
+        getattr(lib, name).restype = c_int
     lib.pfr_mlp_create.argtypes = [c_int, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), c_double, c_double,
                                    c_double_p, c_double_p, ctypes.POINTER(c_void_p)]
     lib.pfr_mlp_destroy.argtypes = [c_void_p]

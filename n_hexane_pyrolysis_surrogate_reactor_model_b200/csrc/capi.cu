@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -19,11 +21,12 @@
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_train.cuh"
+#include "sweep_order.cuh"
 
 using namespace pfr;
 
 static thread_local char g_cuda_err[256] = "";
-static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py reports it)
+static std::atomic<unsigned long long> g_launches{0};  // kernels launched by this library (bench.py reports it)
 
 static int cuda_fail(cudaError_t e, const char* where) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
@@ -47,6 +50,7 @@ struct crnn_model {
 };
 
 struct pfr_mlp {
+    int device;  // the device that holds the weights
     int in_dim;
     int npad4;  // output layer padded to a multiple of GEMM_BM
     float *W1, *b1, *Wt2, *b2, *Wt3, *b3, *Wt4, *b4;
@@ -93,22 +97,85 @@ static inline float host_rn_tf32(float x) {  // round to nearest (ties away) on 
     return x;
 }
 
-// log / exp tables of fastmath.cuh, computed once per process in long double and kept in device memory
-static FastTables* g_tables = nullptr;
-static int ensure_tables() {
-    if (g_tables) return PFR_OK;
-    FastTables h;
-    for (int i = 0; i < LOGTAB_N; i++) {
-        const long double c = 1.0L + ((long double)i + 0.5L) / LOGTAB_N;
-        const double inv = (double)(1.0L / c);
-        h.logtab[i].x = inv;
-        h.logtab[i].y = (double)(-logl((long double)inv));
+// ------------------------------------------------------------------------------------------------
+// Per-DEVICE library state.  Everything the library itself keeps on a GPU -- the log / exp tables of fastmath.cuh, the work-queue
+// counters of the explicit integrators, the auxiliary streams and fork / join events of the MLP chunk pipeline, the opt-in to
+// more than 48 KB of dynamic shared memory (a per-device function attribute) -- lives in the context of the device that is
+// current when a call arrives, created on first use under a mutex.  Handles that own device memory (pfr_mlp, pfr_mlp_trainer,
+// pfr_sweep) record their device, and a call that arrives with another device current returns PFR_EINVAL.
+constexpr int MAX_DEVICES = 64, COUNTER_RING = 64, AUX_STREAMS = 4;
+struct DeviceCtx {
+    bool ready = false;
+    int num_sms = 0;
+    FastTables* tables = nullptr;
+    int* counters = nullptr;                  // ring of work-queue counters: launches in flight on different streams do not share one
+    std::atomic<unsigned> next_counter{0};
+    cudaStream_t aux[AUX_STREAMS] = {};       // second lane of the MLP chunk pipeline, round robin over calls
+    cudaEvent_t fork[AUX_STREAMS] = {}, join[AUX_STREAMS] = {};
+    std::atomic<unsigned> next_aux{0};
+};
+static DeviceCtx g_ctx[MAX_DEVICES];
+static std::mutex g_ctx_mutex;
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PFR_OK;
+}
+
+static int current_device(int* dev) {
+    CK(cudaGetDevice(dev));
+    if (*dev < 0 || *dev >= MAX_DEVICES) return PFR_EINVAL;
+    return PFR_OK;
+}
+
+static int device_ctx(DeviceCtx** out) {
+    int dev = 0, rc;
+    if ((rc = current_device(&dev))) return rc;
+    DeviceCtx& c = g_ctx[dev];
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    if (!c.ready) {
+        CK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        // log / exp tables, computed in long double
+        FastTables h;
+        for (int i = 0; i < LOGTAB_N; i++) {
+            const long double cc = 1.0L + ((long double)i + 0.5L) / LOGTAB_N;
+            const double inv = (double)(1.0L / cc);
+            h.logtab[i].x = inv;
+            h.logtab[i].y = (double)(-logl((long double)inv));
+        }
+        for (int j = 0; j < EXPTAB_N; j++) h.exptab[j] = (double)powl(2.0L, (long double)j / EXPTAB_N);
+        CK(cudaMalloc((void**)&c.tables, sizeof(FastTables)));
+        CK(cudaMemcpy(c.tables, &h, sizeof(FastTables), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&c.counters, COUNTER_RING * sizeof(int)));
+        for (int i = 0; i < AUX_STREAMS; i++) {
+            CK(cudaStreamCreateWithFlags(&c.aux[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming));
+        }
+        // kernels that need more than 48 KB of dynamic shared memory
+        if ((rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true>, tc::SMEM_DYN)) ||
+            (rc = opt_in_smem(dp54_kernel<double>, dp54_smem_bytes<double>())) || (rc = opt_in_smem(dp54_kernel<float>, dp54_smem_bytes<float>())) ||
+            (rc = opt_in_smem(rodas4_kernel<double, true, true>, (size_t)sm_entries<true>() * RODAS_BLOCK * sizeof(double))) ||
+            (rc = opt_in_smem(rodas4_kernel<double, false, true>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(double))) ||
+            (rc = opt_in_smem(rodas4_kernel<double, false, false>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(double))) ||
+            (rc = opt_in_smem(rodas4_kernel<float, true, true>, (size_t)sm_entries<true>() * RODAS_BLOCK * sizeof(float))) ||
+            (rc = opt_in_smem(rodas4_kernel<float, false, true>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(float))) ||
+            (rc = opt_in_smem(rodas4_kernel<float, false, false>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(float))))
+            return rc;
+        c.ready = true;
     }
-    for (int j = 0; j < EXPTAB_N; j++) h.exptab[j] = (double)powl(2.0L, (long double)j / EXPTAB_N);
-    FastTables* d = nullptr;
-    CK(cudaMalloc((void**)&d, sizeof(FastTables)));
-    CK(cudaMemcpy(d, &h, sizeof(FastTables), cudaMemcpyHostToDevice));
-    g_tables = d;
+    *out = &c;
+    return PFR_OK;
+}
+
+static int check_device(int owner) {
+    int dev = 0, rc;
+    if ((rc = current_device(&dev))) return rc;
+    if (dev != owner) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "handle belongs to device %d, but device %d is current", owner, dev);
+        return PFR_EINVAL;
+    }
     return PFR_OK;
 }
 
@@ -137,17 +204,10 @@ extern "C" const char* pfr_status_string(int code) {
     }
 }
 extern "C" const char* pfr_last_cuda_error(void) { return g_cuda_err; }
-extern "C" unsigned long long pfr_launch_count(void) { return g_launches; }
+extern "C" unsigned long long pfr_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out) {
-    if (!w_in || !w_b || !w_out || !out) return PFR_EINVAL;
-    crnn_model* m = new (std::nothrow) crnn_model;
-    if (!m) return PFR_EINVAL;
-    const double def[6] = {1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5};
-    const double* c = clamps ? clamps : def;
-    // the reference holds R_kcal as a float32 tensor / rounds it to float32 in the multiply
-    const float Rk = 1.9872036e-3f;
+static void crnn_model_fill(crnn_model* m, const float* w_in, const float* w_b, const float* w_out) {
     for (int k = 0; k < NS; k++)
         for (int j = 0; j < NR; j++) {
             m->pd.nu[k][j] = (double)w_in[k * NR + j];
@@ -163,12 +223,32 @@ extern "C" int crnn_model_create(const float* w_in, const float* w_b, const floa
         m->pd.lnA[j] = (double)w_b[j];
         m->pf.lnA[j] = w_b[j];
     }
+}
+
+extern "C" int crnn_model_create(const float* w_in, const float* w_b, const float* w_out, const double* clamps, crnn_model_t* out) {
+    if (!w_in || !w_b || !w_out || !out) return PFR_EINVAL;
+    crnn_model* m = new (std::nothrow) crnn_model;
+    if (!m) return PFR_EINVAL;
+    const double def[6] = {1.0e-6, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5};
+    const double* c = clamps ? clamps : def;
+    // the reference holds R_kcal as a float32 tensor / rounds it to float32 in the multiply
+    const float Rk = 1.9872036e-3f;
+    crnn_model_fill(m, w_in, w_b, w_out);
     m->pd.lb = c[0]; m->pd.ub = c[1]; m->pd.zlo = c[2]; m->pd.zhi = c[3]; m->pd.dulo = c[4]; m->pd.duhi = c[5];
     m->pf.lb = (float)c[0]; m->pf.ub = (float)c[1]; m->pf.zlo = (float)c[2]; m->pf.zhi = (float)c[3];
     m->pf.dulo = (float)c[4]; m->pf.duhi = (float)c[5];
     m->pd.inv_R = 1.0 / (double)Rk;
     m->pf.inv_R = 1.0f / Rk;
     *out = m;
+    return PFR_OK;
+}
+
+// The parameters travel to the kernels BY VALUE (a __grid_constant__ argument copied at launch time), so a model handle holds no
+// device memory: new parameters take effect with the next launch and launches already enqueued keep the values they were
+// given.  The training loop calls this once per optimisation step instead of creating and destroying a handle.
+extern "C" int crnn_model_update(crnn_model_t m, const float* w_in, const float* w_b, const float* w_out) {
+    if (!m || !w_in || !w_b || !w_out) return PFR_EINVAL;
+    crnn_model_fill(m, w_in, w_b, w_out);
     return PFR_OK;
 }
 
@@ -192,6 +272,10 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
     pfr_mlp* m = new (std::nothrow) pfr_mlp;
     if (!m) return PFR_EINVAL;
     memset(m, 0, sizeof(*m));
+    {
+        const int rc = current_device(&m->device);
+        if (rc) { delete m; return rc; }
+    }
     m->in_dim = in_dim;
     m->npad4 = round_up(MLP_OUT, GEMM_BM);
     // `out * (max - min) + min`: (max - min) in double, both scalars rounded to float32 by the tensor op
@@ -243,6 +327,10 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
 
 extern "C" int pfr_mlp_set_mode(pfr_mlp_t m, int mode) {
     if (!m || (mode != PFR_MLP_FP32 && mode != PFR_MLP_TF32X3)) return PFR_EINVAL;
+    {
+        const int rc = check_device(m->device);
+        if (rc) return rc;
+    }
     if (mode == PFR_MLP_TF32X3) {
         for (int l = 0; l < 3; l++) {
             const int rows = l < 2 ? MLP_HID : MLP_OUT;
@@ -293,34 +381,32 @@ extern "C" int pfr_dev_set_tc_trace(unsigned long long* l2, unsigned long long* 
     return PFR_OK;
 }
 template <bool kFinal>
-static int launch_tc_gemm(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
+static int launch_tc_gemm(const DeviceCtx& ctx, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
                           const tc::GemmArgs& g, cudaStream_t st) {
     auto kern = tc::mlp_tc_gemm_kernel<kFinal>;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaFuncSetAttribute(tc::mlp_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_DYN));
-        CK(cudaFuncSetAttribute(tc::mlp_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_DYN));
-    }
     const int total = g.n_tiles * g.m_tiles;
-    kern<<<total < num_sms ? total : num_sms, tc::THREADS, tc::SMEM_DYN, st>>>(ahi, alo, bhi, blo, g);   // persistent: one CTA per SM
+    kern<<<total < ctx.num_sms ? total : ctx.num_sms, tc::THREADS, tc::SMEM_DYN, st>>>(ahi, alo, bhi, blo, g);   // persistent: one CTA per SM
     CK_LAUNCH("mlp_tc_gemm_kernel");
     return PFR_OK;
 }
-
-// Auxiliary streams for the two-lane chunk pipeline of mlp_run_tc (round robin over calls, so that concurrent passes on
-// different caller streams do not queue behind each other on one auxiliary stream)
-static cudaStream_t g_mlp_aux[4] = {nullptr, nullptr, nullptr, nullptr};
-static int g_mlp_aux_next = 0;
 
 // Chunks alternate between two lanes (each with its own activation buffers, half of the workspace): lane 0 runs on the
 // caller's stream, lane 1 on an auxiliary stream forked from / joined to it by events.  The GEMM kernels of the two lanes
 // take the SMs in turn (one persistent CTA per SM with ~210 KB of shared memory), while the HBM-bound kernels of one lane
 // (first layer, enforce_strict) run beside the other lane's GEMM CTAs instead of in front of them.
+// The auxiliary stream and its fork / join events belong to the device context (round robin over calls, so that concurrent
+// passes on different caller streams do not queue behind each other on one auxiliary stream); whatever happens inside the
+// chunk loop, the auxiliary stream is joined back to the caller's stream before this function returns.
+static int mlp_run_tc_chunks(DeviceCtx& ctx, pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
+                             float* t_end, bool is_time, int raw, float* const* Ahi, float* const* Alo, float* const* Bhi, float* const* Blo,
+                             float* const* Sl, const CUtensorMap (*mA)[2][2], int ld, int lanes, const cudaStream_t* lane_stream);
+
 static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
                       float* t_end, bool is_time, int raw, float* H, float* S, int ld_full, cudaStream_t st) {
+    DeviceCtx* ctxp = nullptr;
+    int rc0 = device_ctx(&ctxp);
+    if (rc0) return rc0;
+    DeviceCtx& ctx = *ctxp;
     const bool two = n > ld_full / 2 && ld_full % (2 * tc::BM) == 0;
     const int ld = two ? ld_full / 2 : ld_full;
     const int lanes = two ? 2 : 1;
@@ -339,16 +425,27 @@ static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* 
             return rc;
     }
     cudaStream_t lane_stream[2] = {st, st};
-    cudaEvent_t fork = nullptr, join = nullptr;
+    unsigned slot = 0;
     if (two) {
-        cudaStream_t& aux = g_mlp_aux[g_mlp_aux_next++ & 3];
-        if (!aux) CK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-        lane_stream[1] = aux;
-        CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-        CK(cudaEventRecord(fork, st));
-        CK(cudaStreamWaitEvent(aux, fork, 0));
+        slot = ctx.next_aux.fetch_add(1) % AUX_STREAMS;
+        lane_stream[1] = ctx.aux[slot];
+        CK(cudaEventRecord(ctx.fork[slot], st));
+        CK(cudaStreamWaitEvent(ctx.aux[slot], ctx.fork[slot], 0));
     }
+    rc = mlp_run_tc_chunks(ctx, m, T, P, L, U, n, grid, t_end, is_time, raw, Ahi, Alo, Bhi, Blo, Sl, mA, ld, lanes, lane_stream);
+    if (two) {   // join on every path, error or not: the caller's stream must not run ahead of the auxiliary lane
+        cudaError_t e1 = cudaEventRecord(ctx.join[slot], lane_stream[1]);
+        cudaError_t e2 = cudaStreamWaitEvent(st, ctx.join[slot], 0);
+        if (rc == PFR_OK && e1 != cudaSuccess) return cuda_fail(e1, "cudaEventRecord(join)");
+        if (rc == PFR_OK && e2 != cudaSuccess) return cuda_fail(e2, "cudaStreamWaitEvent(join)");
+    }
+    return rc;
+}
+
+static int mlp_run_tc_chunks(DeviceCtx& ctx, pfr_mlp_t m, const float* T, const float* P, const float* L, const float* U, int n, float* grid,
+                             float* t_end, bool is_time, int raw, float* const* Ahi, float* const* Alo, float* const* Bhi, float* const* Blo,
+                             float* const* Sl, const CUtensorMap (*mA)[2][2], int ld, int lanes, const cudaStream_t* lane_stream) {
+    int rc;
     const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
     int ci = 0;
     for (int c0 = 0; c0 < n; c0 += ld, ci++) {
@@ -363,13 +460,13 @@ static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* 
         CK_LAUNCH("mlp_tc_layer1_kernel");
         const int mt = rows / tc::BM;
         tc::GemmArgs g2{m->b2, Bhi[l], Blo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[0]};
-        if ((rc = launch_tc_gemm<false>(mA[l][0][0], mA[l][0][1], m->mapWhi[0], m->mapWlo[0], g2, ls))) return rc;
+        if ((rc = launch_tc_gemm<false>(ctx, mA[l][0][0], mA[l][0][1], m->mapWhi[0], m->mapWlo[0], g2, ls))) return rc;
         tc::GemmArgs g3{m->b3, Ahi[l], Alo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[1]};
-        if ((rc = launch_tc_gemm<false>(mA[l][1][0], mA[l][1][1], m->mapWhi[1], m->mapWlo[1], g3, ls))) return rc;
+        if ((rc = launch_tc_gemm<false>(ctx, mA[l][1][0], mA[l][1][1], m->mapWhi[1], m->mapWlo[1], g3, ls))) return rc;
         float* out_rows = grid ? grid + (size_t)n + c0 : Sl[l];
         const size_t out_ld = grid ? (size_t)n : (size_t)ld;
         tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin, (MLP_OUT + tc::BN - 1) / tc::BN, mt, g_tc_trace[2]};
-        if ((rc = launch_tc_gemm<true>(mA[l][0][0], mA[l][0][1], m->mapWhi[2], m->mapWlo[2], g4, ls))) return rc;
+        if ((rc = launch_tc_gemm<true>(ctx, mA[l][0][0], mA[l][0][1], m->mapWhi[2], m->mapWlo[2], g4, ls))) return rc;
         if (is_time) {
             if (!raw) {
                 enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, ls>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,
@@ -383,12 +480,6 @@ static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* 
             CK_LAUNCH("copy_row_kernel");
         }
     }
-    if (two) {
-        CK(cudaEventRecord(join, lane_stream[1]));
-        CK(cudaStreamWaitEvent(st, join, 0));
-        CK(cudaEventDestroy(fork));
-        CK(cudaEventDestroy(join));
-    }
     return PFR_OK;
 }
 
@@ -397,6 +488,10 @@ static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, 
                    float* t_end, bool is_time, int raw, void* ws, size_t ws_bytes, int chunk, cudaStream_t st) {
     if (n == 0) return PFR_OK;
     if (!m || !T || !P || n < 0 || (!grid && !t_end) || !ws) return PFR_EINVAL;
+    {
+        const int rc = check_device(m->device);
+        if (rc) return rc;
+    }
     const int ld = eff_chunk(n, chunk);
     if (ws_bytes < (4 * (size_t)MLP_HID + (size_t)MLP_OUT) * ld * sizeof(float)) return PFR_EWORKSPACE;
     float* H1 = static_cast<float*>(ws);
@@ -510,12 +605,7 @@ template <typename real, bool kRamp, bool kKnots>
 static int launch_rodas(const CrnnParams<real>& p, const RodasArgs& a, cudaStream_t st) {
     auto kern = rodas4_kernel<real, kRamp, kKnots>;
     const size_t smem = (size_t)sm_entries<kRamp>() * RODAS_BLOCK * sizeof(real);
-    static bool configured = false;  // per template instantiation
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    kern<<<(a.n + RODAS_BLOCK - 1) / RODAS_BLOCK, RODAS_BLOCK, smem, st>>>(p, a);
+    kern<<<(a.n + RODAS_BLOCK - 1) / RODAS_BLOCK, RODAS_BLOCK, smem, st>>>(p, a);   // (shared-memory opt-in: device_ctx)
     CK_LAUNCH("rodas4_kernel");
     return PFR_OK;
 }
@@ -544,23 +634,21 @@ static int dispatch_rodas_coop(const CrnnParams<real>& p, const RodasArgs& a, cu
     return launch_rodas_coop<real, false, false, kMethod>(p, a, st);
 }
 
-// work-queue counters of bs23_kernel: a small ring so that launches in flight on different streams do not share one
-static int* g_bs23_counters = nullptr;
-static int g_bs23_next = 0, g_num_sms = 0;
-constexpr int BS23_COUNTER_RING = 64;
+// bs23_kernel / dp54_kernel draw their work items from a zero-initialised device counter: one of a small per-device ring, so
+// that launches in flight on different streams do not share one
+static int next_counter(DeviceCtx& ctx, cudaStream_t st, int** out) {
+    int* c = ctx.counters + ctx.next_counter.fetch_add(1) % COUNTER_RING;
+    CK(cudaMemsetAsync(c, 0, sizeof(int), st));
+    *out = c;
+    return PFR_OK;
+}
 
 template <typename real>
-static int dispatch_bs23(const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
-    if (!g_bs23_counters) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaMalloc(&g_bs23_counters, BS23_COUNTER_RING * sizeof(int)));
-    }
+static int dispatch_bs23(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
     RodasArgs a = a0;
-    a.work_counter = g_bs23_counters + (g_bs23_next++ % BS23_COUNTER_RING);
-    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
-    const int full = (a.n + BS23_BLOCK - 1) / BS23_BLOCK, persistent = BS23_CTAS_PER_SM * g_num_sms;
+    int rc = next_counter(ctx, st, &a.work_counter);
+    if (rc) return rc;
+    const int full = (a.n + BS23_BLOCK - 1) / BS23_BLOCK, persistent = BS23_CTAS_PER_SM * ctx.num_sms;
     const int grid = full < persistent ? full : persistent;
     if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
     else bs23_kernel<real, false><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
@@ -569,22 +657,11 @@ static int dispatch_bs23(const CrnnParams<real>& p, const RodasArgs& a0, cudaStr
 }
 
 template <typename real>
-static int dispatch_dp54(const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
-    if (!g_bs23_counters) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaMalloc(&g_bs23_counters, BS23_COUNTER_RING * sizeof(int)));
-    }
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        CK(cudaFuncSetAttribute(dp54_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp54_smem_bytes<real>()));
-        configured = true;
-    }
+static int dispatch_dp54(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
     RodasArgs a = a0;
-    a.work_counter = g_bs23_counters + (g_bs23_next++ % BS23_COUNTER_RING);
-    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
-    const int full = (a.n + DP54_BLOCK - 1) / DP54_BLOCK, persistent = DP54_CTAS_PER_SM * g_num_sms;
+    int rc = next_counter(ctx, st, &a.work_counter);
+    if (rc) return rc;
+    const int full = (a.n + DP54_BLOCK - 1) / DP54_BLOCK, persistent = DP54_CTAS_PER_SM * ctx.num_sms;
     dp54_kernel<real><<<full < persistent ? full : persistent, DP54_BLOCK, dp54_smem_bytes<real>(), st>>>(p, a);
     CK_LAUNCH("dp54_kernel");
     return PFR_OK;
@@ -597,6 +674,23 @@ static int dispatch_dopri5(const CrnnParams<real>& p, const Dopri5Args& a, cudaS
     else dopri5_kernel<real, false><<<grid, DOPRI_BLOCK, 0, st>>>(p, a);
     CK_LAUNCH("dopri5_kernel");
     return PFR_OK;
+}
+
+// One integrator launch for fully prepared arguments (pfr_integrate and the sweep pipeline share it)
+static int integrate_launch(DeviceCtx& ctx, crnn_model_t m, int method, int precision, const RodasArgs& a, cudaStream_t st) {
+    const bool d = precision == 64;
+    switch (method) {
+        case PFR_METHOD_RODAS4: return d ? dispatch_rodas_coop<double, COOP_RODAS4>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_RODAS4>(m->pf, a, st);
+        case PFR_METHOD_ROS3: return d ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
+        case PFR_METHOD_DP54: return d ? dispatch_dp54<double>(ctx, m->pd, a, st) : dispatch_dp54<float>(ctx, m->pf, a, st);
+        case PFR_METHOD_BS23: return d ? dispatch_bs23<double>(ctx, m->pd, a, st) : dispatch_bs23<float>(ctx, m->pf, a, st);
+        case PFR_METHOD_RODAS4_TPC: return d ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
+        case PFR_METHOD_DOPRI5: {
+            Dopri5Args da{a.n, a.T0, a.c0, a.tgrid, a.Tprof, a.t_end, a.idx_end, a.perm, a.rtol, a.atol, a.y_out, a.y_dense, a.status, a.stats, a.max_steps};
+            return d ? dispatch_dopri5<double>(m->pd, da, st) : dispatch_dopri5<float>(m->pf, da, st);
+        }
+    }
+    return PFR_EINVAL;
 }
 
 extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0,
@@ -612,33 +706,221 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
     if (max_steps <= 0) max_steps = 1000000;
+    DeviceCtx* ctx = nullptr;
     {
-        const int rc = ensure_tables();
+        const int rc = device_ctx(&ctx);
         if (rc != PFR_OK) return rc;
     }
+    RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, ctx->tables, flags};
+    return integrate_launch(*ctx, m, method, precision, a, (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The whole hot path of one model variant as ONE call (main() sweep loops of SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:
+// 339-369 and ...Eon_single_model.py:296-368): visiting order -> inlet concentration -> MLP passes (the independent passes of the
+// coupled path on two side streams) -> idx_cut -> integrator -> Rosenbrock fallback for conditions the explicit fast path
+// flagged stiff (list and count stay on the device: nothing here waits for the host) -> results in the caller's order.
+struct pfr_sweep {
+    int device, n_max;
+    crnn_model_t crnn;
+    pfr_mlp_t time_mlp, temp_mlp;
+    float *Ts, *Ps, *Ls, *Us, *c0, *t_end, *t_full, *Tprof;
+    int *order, *idx, *hist, *cursor, *stiff_list, *stiff_count;
+    void* ws[3];
+    size_t ws_bytes;
+    cudaStream_t side[2];
+    cudaEvent_t ready, done[2], k0, k1;
+    bool timed;   // k0 / k1 have been recorded by a run
+};
+
+extern "C" int pfr_sweep_destroy(pfr_sweep_t s) {
+    if (!s) return PFR_OK;
+    void* ptrs[] = {s->Ts, s->Ps, s->Ls, s->Us, s->c0, s->t_end, s->t_full, s->Tprof, s->order, s->idx, s->hist, s->cursor,
+                    s->stiff_list, s->stiff_count, s->ws[0], s->ws[1], s->ws[2]};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (s->side[i]) cudaStreamDestroy(s->side[i]);
+        if (s->done[i]) cudaEventDestroy(s->done[i]);
+    }
+    if (s->ready) cudaEventDestroy(s->ready);
+    if (s->k0) cudaEventDestroy(s->k0);
+    if (s->k1) cudaEventDestroy(s->k1);
+    delete s;
+    return PFR_OK;
+}
+
+extern "C" int pfr_sweep_create(crnn_model_t crnn, pfr_mlp_t time_mlp, pfr_mlp_t temp_mlp, int n_max, pfr_sweep_t* out) {
+    if (!crnn || !time_mlp || time_mlp->in_dim != 4 || (temp_mlp && temp_mlp->in_dim != 2) || n_max < 1 || !out) return PFR_EINVAL;
+    pfr_sweep* s = new (std::nothrow) pfr_sweep();
+    if (!s) return PFR_EINVAL;
+    memset(s, 0, sizeof(*s));
+    int rc = current_device(&s->device);
+    if (rc == PFR_OK) rc = check_device(time_mlp->device);
+    if (rc == PFR_OK && temp_mlp) rc = check_device(temp_mlp->device);
+    if (rc) { delete s; return rc; }
+    s->n_max = n_max;
+    s->crnn = crnn;
+    s->time_mlp = time_mlp;
+    s->temp_mlp = temp_mlp;
+    const size_t n = (size_t)n_max;
+    s->ws_bytes = pfr_mlp_workspace_bytes(n_max, 0);
+    const int passes = temp_mlp ? 3 : 1;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc((void**)&s->Ts, n * 4); alloc((void**)&s->Ps, n * 4); alloc((void**)&s->Ls, n * 4); alloc((void**)&s->Us, n * 4);
+    alloc((void**)&s->c0, n * 4); alloc((void**)&s->t_end, n * 4);
+    alloc((void**)&s->order, n * 4); alloc((void**)&s->idx, n * 4); alloc((void**)&s->stiff_list, n * 4);
+    alloc((void**)&s->hist, ORDER_BINS * 4); alloc((void**)&s->cursor, ORDER_BINS * 4); alloc((void**)&s->stiff_count, 4);
+    if (temp_mlp) { alloc((void**)&s->t_full, n * NTOT * 4); alloc((void**)&s->Tprof, n * NTOT * 4); }
+    for (int i = 0; i < passes; i++) alloc(&s->ws[i], s->ws_bytes);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->k0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->k1);
+    if (e == cudaSuccess) e = cudaMemset(s->stiff_count, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        pfr_sweep_destroy(s);
+        return cuda_fail(e, "pfr_sweep_create");
+    }
+    *out = s;
+    return PFR_OK;
+}
+
+extern "C" size_t pfr_sweep_device_bytes(int n_max, int energy_on) {
+    const size_t n = (size_t)(n_max < 1 ? 1 : n_max);
+    return n * 4 * 9 + (energy_on ? 2 * n * NTOT * 4 : 0) + (energy_on ? 3 : 1) * pfr_mlp_workspace_bytes(n_max, 0) + 2 * ORDER_BINS * 4 + 4;
+}
+
+extern "C" int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, const float* L, const float* u0, int n, int method, int precision,
+                             double rtol, double atol, int max_steps, int flags, void* y_out, int* status, int* stats, int* idx_cut_out,
+                             float* t_end_out, int* stiff_count_out, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!s || !T || !P || !y_out || !status || n < 0 || n > s->n_max) return PFR_EINVAL;
+    if ((L == nullptr) != (u0 == nullptr)) return PFR_EINVAL;
+    if (precision != 32 && precision != 64) return PFR_EINVAL;
+    if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
+    const bool eon = s->temp_mlp != nullptr;
+    if (eon ? (method != PFR_METHOD_BS23 && method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4)
+            : (method != PFR_METHOD_DP54 && method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4))
+        return PFR_EINVAL;
+    if (!eon && !L) return PFR_EINVAL;   // the isothermal sweep integrates to the end of the (T, P, L, u0) grid
+    int rc = check_device(s->device);
+    if (rc) return rc;
+    DeviceCtx* ctx = nullptr;
+    if ((rc = device_ctx(&ctx))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (method == PFR_METHOD_RODAS4) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_rodas_coop<double, COOP_RODAS4>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_RODAS4>(m->pf, a, st);
+    if (max_steps <= 0) max_steps = 1000000;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+
+    // 1. visiting order (cost proxy known before the MLPs run) and the inputs gathered into it
+    const MlpInputScale& sc = s->time_mlp->sc;
+    const bool ordered = !(flags & PFR_SWEEP_NO_ORDER) && (eon ? L != nullptr : true);
+    const float *Tv = T, *Pv = P, *Lv = L, *Uv = u0;
+    const int* order = nullptr;
+    if (ordered) {
+        OrderKey key;
+        if (eon) {   // residence-time ratio L / u0
+            const float lo = sc.lo[2] / (sc.lo[3] + sc.span[3]), hi = (sc.lo[2] + sc.span[2]) / sc.lo[3];
+            key = {L, u0, lo, (float)ORDER_BINS / (hi - lo)};
+        } else {     // inlet temperature
+            key = {T, nullptr, sc.lo[0], (float)ORDER_BINS / sc.span[0]};
+        }
+        CK(cudaMemsetAsync(s->hist, 0, ORDER_BINS * sizeof(int), st));
+        order_hist_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(key, n, s->hist);
+        CK_LAUNCH("order_hist_kernel");
+        order_scan_kernel<<<1, ORDER_BINS / 2, 0, st>>>(s->hist, s->cursor);
+        CK_LAUNCH("order_scan_kernel");
+        order_scatter_kernel<<<blocks, 256, 0, st>>>(key, n, s->cursor, s->order, T, P, L, u0, s->Ts, s->Ps, s->Ls, s->Us);
+        CK_LAUNCH("order_scatter_kernel");
+        Tv = s->Ts; Pv = s->Ps; Lv = L ? s->Ls : nullptr; Uv = u0 ? s->Us : nullptr;
+        order = s->order;
     }
-    if (method == PFR_METHOD_ROS3) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
+    // 2. inlet concentration
+    if ((rc = pfr_inlet_concentration(Tv, Pv, n, s->c0, st))) return rc;
+
+    RodasArgs a{n, Tv, s->c0, nullptr, nullptr, nullptr, nullptr, nullptr, rtol, atol, y_out, nullptr, status, stats, max_steps, ctx->tables, 0};
+    a.out_index = order;
+    if (eon) {
+        // 3. the three MLP passes are independent: temperature profile and outlet time on the side streams, the full-length grid
+        //    on the caller's stream (GEMM CTAs fill the SMs one kernel at a time; the HBM-bound kernels between them overlap)
+        CK(cudaEventRecord(s->ready, st));
+        CK(cudaStreamWaitEvent(s->side[0], s->ready, 0));
+        rc = pfr_temp_profile(s->temp_mlp, Tv, Pv, n, s->Tprof, 0, s->ws[1], s->ws_bytes, 0, s->side[0]);
+        cudaError_t e0 = cudaEventRecord(s->done[0], s->side[0]);
+        int rc2 = PFR_OK;
+        cudaError_t e1 = cudaSuccess;
+        if (L) {
+            CK(cudaStreamWaitEvent(s->side[1], s->ready, 0));
+            rc2 = pfr_time_grid(s->time_mlp, Tv, Pv, Lv, Uv, n, nullptr, s->t_end, 0, s->ws[2], s->ws_bytes, 0, s->side[1]);
+            e1 = cudaEventRecord(s->done[1], s->side[1]);
+        }
+        int rc3 = pfr_time_grid(s->time_mlp, Tv, Pv, nullptr, nullptr, n, s->t_full, L ? nullptr : s->t_end, 0, s->ws[0], s->ws_bytes, 0, st);
+        // join on every path before reporting an error
+        cudaError_t e2 = cudaStreamWaitEvent(st, s->done[0], 0);
+        cudaError_t e3 = L ? cudaStreamWaitEvent(st, s->done[1], 0) : cudaSuccess;
+        if (rc || rc2 || rc3) return rc ? rc : (rc2 ? rc2 : rc3);
+        for (cudaError_t e : {e0, e1, e2, e3})
+            if (e != cudaSuccess) return cuda_fail(e, "pfr_sweep_run: stream join");
+        // 4. outlet knot
+        if (L) {
+            idx_cut_kernel<<<blocks, 256, 0, st>>>(s->t_full, (size_t)n, s->t_end, n, s->idx);
+            CK_LAUNCH("idx_cut_kernel");
+        } else {
+            fill_int_kernel<<<blocks, 256, 0, st>>>(s->idx, n, NTOT - 1);
+            CK_LAUNCH("fill_int_kernel");
+        }
+        a.tgrid = s->t_full;
+        a.Tprof = s->Tprof;
+        a.idx_end = s->idx;
+    } else {
+        if ((rc = pfr_time_grid(s->time_mlp, Tv, Pv, Lv, Uv, n, nullptr, s->t_end, 0, s->ws[0], s->ws_bytes, 0, st))) return rc;
+        a.t_end = s->t_end;
     }
-    if (method == PFR_METHOD_DP54) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_dp54<double>(m->pd, a, st) : dispatch_dp54<float>(m->pf, a, st);
+    // 5. the integrator (timed by a pair of events that belong to the handle)
+    CK(cudaEventRecord(s->k0, st));
+    if ((rc = integrate_launch(*ctx, s->crnn, method, precision, a, st))) return rc;
+    CK(cudaEventRecord(s->k1, st));
+    s->timed = true;
+    // 6. conditions the explicit fast path flagged stiff go through the Rosenbrock kernel; the list is built and counted on the device
+    if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_DP54) && !(flags & PFR_SWEEP_NO_FALLBACK)) {
+        int* count = stiff_count_out ? stiff_count_out : s->stiff_count;
+        CK(cudaMemsetAsync(count, 0, sizeof(int), st));
+        collect_status_kernel<<<blocks, 256, 0, st>>>(status, order, n, PFR_ST_STIFF, s->stiff_list, count);
+        CK_LAUNCH("collect_status_kernel");
+        RodasArgs f = a;
+        f.perm = s->stiff_list;
+        f.n_work = count;
+        if ((rc = integrate_launch(*ctx, s->crnn, eon ? PFR_METHOD_ROS3 : PFR_METHOD_RODAS4, precision, f, st))) return rc;
     }
-    if (method == PFR_METHOD_BS23) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_bs23<double>(m->pd, a, st) : dispatch_bs23<float>(m->pf, a, st);
+    else if (stiff_count_out) CK(cudaMemsetAsync(stiff_count_out, 0, sizeof(int), st));
+    // 7. by-products in the caller's order
+    if (idx_cut_out && eon) {
+        unorder_kernel<int><<<blocks, 256, 0, st>>>(s->idx, order, n, idx_cut_out);
+        CK_LAUNCH("unorder_kernel");
     }
-    if (method == PFR_METHOD_RODAS4_TPC) {
-        RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps, g_tables, flags};
-        return precision == 64 ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
+    if (t_end_out) {
+        unorder_kernel<float><<<blocks, 256, 0, st>>>(s->t_end, order, n, t_end_out);
+        CK_LAUNCH("unorder_kernel");
     }
-    Dopri5Args a{n, T0, c0, tgrid, Tprof, t_end, idx_end, perm, rtol, atol, y_out, y_dense, status, stats, max_steps};
-    return precision == 64 ? dispatch_dopri5<double>(m->pd, a, st) : dispatch_dopri5<float>(m->pf, a, st);
+    return PFR_OK;
+}
+
+extern "C" int pfr_sweep_stiff_count(pfr_sweep_t s, int* count) {
+    if (!s || !count) return PFR_EINVAL;
+    CK(cudaMemcpy(count, s->stiff_count, sizeof(int), cudaMemcpyDeviceToHost));   // synchronises
+    return PFR_OK;
+}
+
+extern "C" int pfr_sweep_integrator_ms(pfr_sweep_t s, float* ms) {
+    if (!s || !ms || !s->timed) return PFR_EINVAL;
+    CK(cudaEventSynchronize(s->k1));
+    CK(cudaEventElapsedTime(ms, s->k0, s->k1));
+    return PFR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -647,11 +929,12 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
                              double* grad, void* stream) {
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || n < 0 || substeps == 0) return PFR_EINVAL;
+    DeviceCtx* ctx = nullptr;
     {
-        const int rc = ensure_tables();
+        const int rc = device_ctx(&ctx);
         if (rc != PFR_OK) return rc;
     }
-    AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad, g_tables};
+    AdjointArgs a{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad, ctx->tables};
     if (substeps > 0) {
         // one condition per warp
         const int blocks = (n + ADJW_WARPS - 1) / ADJW_WARPS;
@@ -679,6 +962,7 @@ extern "C" int pfr_reduce_rows(const double* x, int rows, int n, double* out, vo
 // ------------------------------------------------------------------------------------------------
 // Predictor-MLP training step (mlp_train.cuh)
 struct pfr_mlp_trainer {
+    int device;
     int in_dim;
     long long step;
     float *W[4], *b[4], *mW[4], *vW[4], *mb[4], *vb[4];
@@ -692,6 +976,10 @@ extern "C" int pfr_mlp_trainer_create(int in_dim, const float* const weights[4],
     if (!out || !weights || !biases || (in_dim != 2 && in_dim != 4)) return PFR_EINVAL;
     pfr_mlp_trainer* t = new (std::nothrow) pfr_mlp_trainer();
     if (!t) return PFR_ECUDA;
+    {
+        const int rc = current_device(&t->device);
+        if (rc) { delete t; return rc; }
+    }
     t->in_dim = in_dim;
     t->step = 0;
     for (int l = 0; l < 4; l++) {
@@ -723,6 +1011,10 @@ extern "C" int pfr_mlp_trainer_destroy(pfr_mlp_trainer_t t) {
 
 // fc1..fc4 on at most 32 rows; activations stay in the trainer's buffers (both layouts), the network output in act[3]
 static int trainer_forward32(pfr_mlp_trainer_t t, const float* x, int B, cudaStream_t st) {
+    {
+        const int rc = check_device(t->device);
+        if (rc) return rc;
+    }
     for (int l = 0; l < 4; l++) {
         const int K = tr_K(t, l), N = tr_N(l);
         const float* in = l == 0 ? x : t->actT[l - 1];
@@ -804,9 +1096,10 @@ __global__ void __launch_bounds__(128) fastmath_kernel(const FastTables* __restr
 extern "C" int pfr_fastmath(int kind, int n, const double* x, double* y, void* stream) {
     if (n == 0) return PFR_OK;
     if (!x || !y || n < 0 || (kind != 0 && kind != 1)) return PFR_EINVAL;
-    const int rc = ensure_tables();
+    DeviceCtx* ctx = nullptr;
+    const int rc = device_ctx(&ctx);
     if (rc != PFR_OK) return rc;
-    fastmath_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g_tables, kind, n, x, y);
+    fastmath_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->tables, kind, n, x, y);
     CK_LAUNCH("fastmath_kernel");
     return PFR_OK;
 }

@@ -23,9 +23,15 @@ struct FastTables {
 constexpr double LN2_HI = 6.93147180369123816490e-01;  // fdlibm split: the high part has 21 trailing zero bits
 constexpr double LN2_LO = 1.90821492927058770002e-10;
 
+#ifndef PFR_FAST_MAGIC
+#define PFR_FAST_MAGIC 1   // integer <-> double conversions of log / exp as "magic number" FP64 adds (2^52 + 2^51 shifts the integer
+                           // into the low mantissa word) instead of I2F.F64 / F2I.F64 on the XU pipe: one DADD more per call on the
+                           // FP64 pipe, three conversions fewer per log + exp pair on the (16 lanes / clk) XU pipe
+#endif
+constexpr double MAGIC_52_51 = 6755399441055744.0;   // 2^52 + 2^51: (x + MAGIC) holds rn(x) in its low word for |x| < 2^31
+
 __device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
-    const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);  // [1, 2)
     const double2 t = tab[(hi >> 13) & (LOGTAB_N - 1)];
     const double r = fma(m, t.x, -1.0);
@@ -34,13 +40,24 @@ __device__ __forceinline__ double fast_log(double x, const double2* __restrict__
     p = fma(r, p, 1.0 / 3.0);
     p = fma(r, p, -0.5);
     p = fma(r * r, p, r);
-    const double ed = (double)e;
+#if PFR_FAST_MAGIC
+    // the biased exponent dropped into the low mantissa word of 2^52 is the double 2^52 + (e + 1023), exactly
+    const double ed = __hiloint2double(0x43300000, hi >> 20) - (4503599627370496.0 + 1023.0);
+#else
+    const double ed = (double)((hi >> 20) - 1023);
+#endif
     return fma(ed, LN2_HI, t.y) + fma(ed, LN2_LO, p);
 }
 
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+#if PFR_FAST_MAGIC
+    const double sh = fma(x, 92.33248261689366, MAGIC_52_51);   // 64 / ln 2; the sum is rounded to an integer (ties to even)
+    const int k = __double2loint(sh);
+    const double kd = sh - MAGIC_52_51;
+#else
     const int k = __double2int_rn(x * 92.33248261689366);  // 64 / ln 2
     const double kd = (double)k;
+#endif
     double r = fma(kd, -LN2_HI / 64.0, x);
     r = fma(kd, -LN2_LO / 64.0, r);
     double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);

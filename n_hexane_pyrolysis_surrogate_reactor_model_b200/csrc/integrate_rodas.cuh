@@ -42,6 +42,12 @@ struct RodasArgs {
     const FastTables* tables;  // device copy of the log / exp tables (fastmath.cuh)
     int flags;                 // bit 0: y_dense holds the raw (unclamped) knot states
     int* work_counter = nullptr;  // bs23_kernel: zero-initialised device counter of its lane-level work queue
+    // Sweep pipeline (pfr_sweep_run): the per-condition INPUT arrays above are held in the pipeline's visiting order, results go
+    // back to the caller's order: y_out / status / stats of work item i are written at column out_index[i] (nullptr: i).
+    const int* out_index = nullptr;
+    // Number of work items taken from device memory (the stiff-fallback launch: its list is built on the device and nobody
+    // waits for the host to learn its length); nullptr: n.  Array strides stay n.
+    const int* n_work = nullptr;
 };
 
 namespace rodas4 {
@@ -399,7 +405,7 @@ rodas4_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
         // rows past the last knot reached (idx_end < 800, or a failed trajectory) repeat the final state
         for (int kk = kc + 1; kk < NTOT; kk++)
 #pragma unroll
-            for (int k = 0; k < NS; k++) y_dense[((size_t)kk * NS + k) * n + i] = yf[k];
+            for (int k = 0; k < NS; k++) y_dense[((size_t)kk * NS + k) * n + i] = (a.flags & 1) ? sm[(SM_Y + k) * RODAS_BLOCK] : yf[k];
     }
 }
 

@@ -278,6 +278,9 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
     constexpr double kGamma = kMethod == COOP_ROS3 ? ros3::gamma : rodas4::gamma;
     constexpr double kD1 = kMethod == COOP_ROS3 ? ros3::d1 : rodas4::d1;
     static_assert(!kRamp || kKnots, "a temperature ramp needs knot-limited stepping");
+    // stiff-fallback launch of the sweep pipeline: sized for the whole batch, its (usually empty) list counted on the device --
+    // blocks beyond the list leave before they touch anything
+    if (a.n_work && (long long)blockIdx.x * COOP_PER_BLOCK >= (long long)*a.n_work) return;
     __shared__ __align__(16) CoopParams<real> sp_block;
     CoopParams<real>& sp0 = sp_block;
 #if PFR_AINV_SMEM
@@ -308,10 +311,12 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
     if (mirror) { grp = COOP_PER_WARP - 1; l = lane - 30; }
     const int base = 3 * grp;
     const int first = (blockIdx.x * (COOP_BLOCK / 32) + warp) * COOP_PER_WARP;
-    if (first >= a.n) return;  // warp-uniform
+    const int nwork = a.n_work ? min(*a.n_work, a.n) : a.n;   // (device-side count: the stiff-fallback list of pfr_sweep_run)
+    if (first >= nwork) return;  // warp-uniform
     const int slot = first + grp;
-    const bool writer = !mirror && slot < a.n;
-    const int i = a.perm ? a.perm[slot < a.n ? slot : a.n - 1] : (slot < a.n ? slot : a.n - 1);
+    const bool writer = !mirror && slot < nwork;
+    const int i = a.perm ? a.perm[slot < nwork ? slot : nwork - 1] : (slot < nwork ? slot : nwork - 1);
+    const int io = a.out_index ? a.out_index[i] : i;            // column of the results (caller's order)
     const size_t n = (size_t)a.n;
     real* __restrict__ y_out = static_cast<real*>(a.y_out);
     real* __restrict__ y_dense = static_cast<real*>(a.y_dense);
@@ -611,20 +616,20 @@ rodas4_coop_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a
 #pragma unroll
     for (int m = 0; m < 3; m++) {
         yf[m] = m_min(m_max(y[m], p.lb), p.ub);
-        y_out[(size_t)(3 * m + l) * n + i] = yf[m];
+        y_out[(size_t)(3 * m + l) * n + io] = yf[m];
     }
     if (l == 0) {
-        a.status[i] = status;
+        a.status[io] = status;
         if (a.stats) {
-            a.stats[i] = nacc;
-            a.stats[n + i] = nrej;
-            a.stats[2 * n + i] = nrhs;
+            a.stats[io] = nacc;
+            a.stats[n + io] = nrej;
+            a.stats[2 * n + io] = nrhs;
         }
     }
     if (dense && kc < NTOT - 1) {
         for (int kk = kc + 1; kk < NTOT; kk++)
 #pragma unroll
-            for (int m = 0; m < 3; m++) y_dense[((size_t)kk * NS + 3 * m + l) * n + i] = yf[m];
+            for (int m = 0; m < 3; m++) y_dense[((size_t)kk * NS + 3 * m + l) * n + i] = (a.flags & 1) ? y[m] : yf[m];
     }
 }
 
