@@ -158,7 +158,8 @@ int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, const float* L,
 /* conditions the last run handed to the Rosenbrock fallback: written to stiff_count_out (one int on the device, caller-owned) if
  * given, else kept by the handle and read with this call (which synchronises the device) */
 int pfr_sweep_stiff_count(pfr_sweep_t s, int* count);
-/* device time of the last run's integrator launch, between two events of the handle (waits for that launch to finish) */
+/* mean device time of the integrator launch over the runs since the previous call of this function (at most the last 16; the
+ * last run again if there was none), between event pairs the handle records around it; waits for those launches to finish */
 int pfr_sweep_integrator_ms(pfr_sweep_t s, float* ms);
 
 /* Loss and gradient of one training step for a batch of conditions

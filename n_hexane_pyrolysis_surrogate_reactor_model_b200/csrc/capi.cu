@@ -730,8 +730,11 @@ struct pfr_sweep {
     void* ws[3];
     size_t ws_bytes;
     cudaStream_t side[2];
-    cudaEvent_t ready, done[2], k0, k1;
-    bool timed;   // k0 / k1 have been recorded by a run
+    cudaEvent_t ready, done[2];
+    // integrator timing: a ring of event pairs, one per run; pfr_sweep_integrator_ms averages the runs since its last call
+    static constexpr int TIMING_RING = 16;
+    cudaEvent_t k0[TIMING_RING], k1[TIMING_RING];
+    unsigned long long runs, runs_reported;
 };
 
 extern "C" int pfr_sweep_destroy(pfr_sweep_t s) {
@@ -745,8 +748,10 @@ extern "C" int pfr_sweep_destroy(pfr_sweep_t s) {
         if (s->done[i]) cudaEventDestroy(s->done[i]);
     }
     if (s->ready) cudaEventDestroy(s->ready);
-    if (s->k0) cudaEventDestroy(s->k0);
-    if (s->k1) cudaEventDestroy(s->k1);
+    for (int i = 0; i < pfr_sweep::TIMING_RING; i++) {
+        if (s->k0[i]) cudaEventDestroy(s->k0[i]);
+        if (s->k1[i]) cudaEventDestroy(s->k1[i]);
+    }
     delete s;
     return PFR_OK;
 }
@@ -780,8 +785,10 @@ extern "C" int pfr_sweep_create(crnn_model_t crnn, pfr_mlp_t time_mlp, pfr_mlp_t
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreate(&s->k0);
-    if (e == cudaSuccess) e = cudaEventCreate(&s->k1);
+    for (int i = 0; i < pfr_sweep::TIMING_RING && e == cudaSuccess; i++) {
+        e = cudaEventCreate(&s->k0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->k1[i]);
+    }
     if (e == cudaSuccess) e = cudaMemset(s->stiff_count, 0, sizeof(int));
     if (e != cudaSuccess) {
         pfr_sweep_destroy(s);
@@ -882,10 +889,11 @@ extern "C" int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, cons
         a.t_end = s->t_end;
     }
     // 5. the integrator (timed by a pair of events that belong to the handle)
-    CK(cudaEventRecord(s->k0, st));
+    const int slot = (int)(s->runs % pfr_sweep::TIMING_RING);
+    CK(cudaEventRecord(s->k0[slot], st));
     if ((rc = integrate_launch(*ctx, s->crnn, method, precision, a, st))) return rc;
-    CK(cudaEventRecord(s->k1, st));
-    s->timed = true;
+    CK(cudaEventRecord(s->k1[slot], st));
+    s->runs++;
     // 6. conditions the explicit fast path flagged stiff go through the Rosenbrock kernel; the list is built and counted on the device
     if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_DP54) && !(flags & PFR_SWEEP_NO_FALLBACK)) {
         int* count = stiff_count_out ? stiff_count_out : s->stiff_count;
@@ -917,9 +925,20 @@ extern "C" int pfr_sweep_stiff_count(pfr_sweep_t s, int* count) {
 }
 
 extern "C" int pfr_sweep_integrator_ms(pfr_sweep_t s, float* ms) {
-    if (!s || !ms || !s->timed) return PFR_EINVAL;
-    CK(cudaEventSynchronize(s->k1));
-    CK(cudaEventElapsedTime(ms, s->k0, s->k1));
+    if (!s || !ms || s->runs == 0) return PFR_EINVAL;
+    unsigned long long first = s->runs_reported;
+    if (first == s->runs) first = s->runs - 1;                                        // nothing new: the last run again
+    if (s->runs - first > pfr_sweep::TIMING_RING) first = s->runs - pfr_sweep::TIMING_RING;
+    double sum = 0;
+    for (unsigned long long r = first; r < s->runs; r++) {
+        const int slot = (int)(r % pfr_sweep::TIMING_RING);
+        float one = 0;
+        CK(cudaEventSynchronize(s->k1[slot]));
+        CK(cudaEventElapsedTime(&one, s->k0[slot], s->k1[slot]));
+        sum += one;
+    }
+    *ms = (float)(sum / (double)(s->runs - first));
+    s->runs_reported = s->runs;
     return PFR_OK;
 }
 

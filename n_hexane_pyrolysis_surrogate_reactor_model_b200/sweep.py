@@ -34,22 +34,50 @@ def shard_bounds(n: int, world_size: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_outlets(y_local, n_total: int, group=None):
-    """All-gather the per-rank [9, n_r] outlet blocks into [9, n_total] on every rank (NCCL on GPUs, gloo on CPU).
-    Blocks may be ragged by one column, so they are padded to a common width for the collective."""
+class GatheredOutlets:
+    """The outlets of every rank after the final gather: one [world, 9, width] buffer (width = ceil(n_total / world)) as the
+    collective filled it.  Rank r's conditions are buf[r, :, :hi_r - lo_r]; `blocks()` hands out those views, `full()`
+    concatenates them into [9, n_total] for callers that want one array (a copy -- the sweep itself never needs it)."""
+
+    def __init__(self, buf, n_total: int):
+        self.buf, self.n_total = buf, n_total
+
+    def blocks(self):
+        ws = self.buf.shape[0]
+        return [self.buf[r, :, : hi - lo] for r, (lo, hi) in ((r, shard_bounds(self.n_total, ws, r)) for r in range(ws))]
+
+    def full(self):
+        import torch
+        return torch.cat(self.blocks(), dim=1)
+
+
+_gather_buffers = {}
+
+
+def gather_outlets(y_local, n_total: int, group=None, as_blocks: bool = False):
+    """The only collective of the sweep: all-gather the per-rank [9, n_r] outlet blocks (NCCL on GPUs, gloo on CPU).
+    One `all_gather_into_tensor` into a buffer [world, 9, width] that is allocated once per (shape, dtype, device) and reused by
+    every sweep -- no per-call zero fill, tensor list or concatenation.  Blocks may be ragged by one column: a rank whose block
+    is narrower than `width` sends it through a persistent staging buffer (the extra column is never read back).
+    Returns [9, n_total] (`as_blocks=False`; single process: `y_local` itself) or the GatheredOutlets view object."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return y_local
+        return GatheredOutlets(y_local.unsqueeze(0), n_total) if as_blocks else y_local
     ws = dist.get_world_size(group)
     width = (n_total + ws - 1) // ws
-    pad = torch.zeros((y_local.shape[0], width), dtype=y_local.dtype, device=y_local.device)
-    pad[:, : y_local.shape[1]] = y_local
-    out = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(out, pad, group=group)
-    parts = []
-    for r in range(ws):
-        lo, hi = shard_bounds(n_total, ws, r)
-        parts.append(out[r][:, : hi - lo])
-    return torch.cat(parts, dim=1)
+    rows = y_local.shape[0]
+    key = (rows, width, ws, y_local.dtype, y_local.device)
+    bufs = _gather_buffers.get(key)
+    if bufs is None:
+        bufs = _gather_buffers[key] = (torch.empty((ws, rows, width), dtype=y_local.dtype, device=y_local.device),
+                                       torch.zeros((rows, width), dtype=y_local.dtype, device=y_local.device))
+    out, stage = bufs
+    send = y_local
+    if y_local.shape[1] != width or not y_local.is_contiguous():
+        stage[:, : y_local.shape[1]].copy_(y_local)
+        send = stage
+    dist.all_gather_into_tensor(out.view(-1), send.reshape(-1), group=group)   # flat views: rank r fills out[r]
+    g = GatheredOutlets(out, n_total)
+    return g if as_blocks else g.full()

@@ -565,9 +565,11 @@ def test_integrators_ragged_batch_sizes(surrogates, conditions, method, precisio
         assert torch.equal(sub.stats, full.stats[:, :n])
 
 
-@pytest.mark.parametrize("mech,variant,method,tol", [("LLNL", "Eon", "bs23", 1e-8), ("JetSurf", "Eoff", "dp54", 1e-7), ("NUIG", "Eon", "bs23", 1e-8),
-                                                     ("LLNL", "Eon", "rodas4", 1e-6), ("JetSurf", "Eoff", "rodas4", 1e-6)])
-def test_full_size_sweep_properties(surrogates, model_sets, mech, variant, method, tol):
+@pytest.mark.parametrize("mech,variant,method,tol,bound", [
+    ("LLNL", "Eon", "bs23", (3e-7, 1e-12), 1e-6),      # the bench headline: the parity-certified setting is held to the parity bound
+    ("JetSurf", "Eoff", "dp54", (1e-7, 1e-7), 2e-4), ("NUIG", "Eon", "bs23", (3e-7, 1e-12), 2e-5),
+    ("LLNL", "Eon", "rodas4", (1e-6, 1e-6), 2e-4), ("JetSurf", "Eoff", "rodas4", (1e-6, 1e-6), 2e-4)])
+def test_full_size_sweep_properties(surrogates, model_sets, mech, variant, method, tol, bound):
     """BASELINE's full size (2^20 Latin-hypercube conditions on one GPU) through size-independent properties:
     every trajectory succeeds; outlets stay inside the clamp interval; carbon and hydrogen are conserved (these
     float32 parameter sets satisfy E^T w_out = 0 to 1e-6..3e-6, which bounds the drift of sum_i E_i y_i by that residual
@@ -580,7 +582,7 @@ def test_full_size_sweep_properties(surrogates, model_sets, mech, variant, metho
     n = 1 << 20
     T, P, L, U = lhs_conditions(n, seed=13895)
     s = surrogates(mech, variant)
-    res = s.sweep(T, P, L, U, method=method, rtol=tol, atol=tol)      # the sweep as bench.py runs it (fast paths) / the Rosenbrock kernel
+    res = s.sweep(T, P, L, U, method=method, rtol=tol[0], atol=tol[1])   # the sweep as bench.py runs it: one library call (pfr_sweep_run)
     assert int((res.status != 0).sum()) == 0 and res.stiff_fallbacks == 0
     y = res.y
     assert float(y.min()) >= 1e-6 and float(y.max()) <= 60.0
@@ -608,8 +610,8 @@ def test_full_size_sweep_properties(surrogates, model_sets, mech, variant, metho
     # ... and the full-size run itself, at its own tolerance, against the same converged solutions (the stage-(B) envelope:
     # tolerance-level error; measured: fast paths 3e-6 .. 1.4e-4 worst case, 5e-8 .. 1.5e-6 median; RODAS4 at 1e-6: 2e-5 .. 5e-5, 1.5e-6 .. 6e-6)
     e = rel_err(res.y[:, torch.as_tensor(sel, device=y.device)].cpu().numpy().T, truth).max(1)
-    print(f"{mech} {variant} {method}@{tol:g}: 256 random LHS conditions vs converged oracle: median {np.median(e):.2e} max {e.max():.2e}")
-    assert e.max() < 2e-4 and np.median(e) < 1e-5
+    print(f"{mech} {variant} {method}@{tol}: 256 random LHS conditions vs converged oracle: median {np.median(e):.2e} max {e.max():.2e}")
+    assert e.max() < bound and np.median(e) < 1e-5
 
 
 @pytest.mark.parametrize("variant", ["Eoff", "Eon"])
