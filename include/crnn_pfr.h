@@ -34,7 +34,7 @@ extern "C" {
 #define PFR_ST_MAXSTEPS 1
 #define PFR_ST_NONFINITE 2
 #define PFR_ST_UNDERFLOW 3
-#define PFR_ST_STIFF 4      /* PFR_METHOD_BS23 only: the explicit fast path met a stiff knot interval; integrate this condition with
+#define PFR_ST_STIFF 4      /* explicit fast paths only (PFR_METHOD_BS23, _BS23_WARP, _DP54): the explicit fast path met a stiff knot interval; integrate this condition with
                             * PFR_METHOD_ROS3 / PFR_METHOD_RODAS4 (Surrogate does so automatically) */
 
 #define PFR_FLAG_DENSE_RAW 1
@@ -51,6 +51,10 @@ extern "C" {
 #define PFR_METHOD_DP54 5       /* explicit Dormand-Prince 5(4), one thread per condition, free stepping to t_end at T = T0 (tgrid,
                                  * Tprof, idx_end, y_dense must be NULL): the fast path of the isothermal (Eoff) sweep; our own
                                  * step-size controller, NOT torchdiffeq's (that is PFR_METHOD_DOPRI5); PFR_ST_STIFF as above */
+
+#define PFR_METHOD_BS23_WARP 6  /* PFR_METHOD_BS23 with ONE CONDITION PER WARP (lane = species = reaction; float64, tgrid required): the
+                                 * latency-oriented mapping for batches of a few hundred conditions with dense output -- the forward
+                                 * pass of the training step; same method and controller, dot products summed in another order */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;
@@ -131,6 +135,14 @@ int pfr_integrate(crnn_model_t m, int method, int precision, int n, const float*
                   double rtol, double atol, int max_steps, int flags, void* y_out, void* y_dense, int* status,
                   int* stats, void* stream);
 
+/* Device-side hand-over of the explicit fast paths: collects the conditions that pfr_integrate(PFR_METHOD_BS23 | PFR_METHOD_DP54) left
+ * with status PFR_ST_STIFF into a list on the device and integrates them again with `method` (PFR_METHOD_ROS3 | PFR_METHOD_RODAS4),
+ * overwriting their y_out / y_dense / status / stats.  Same arrays and meaning as pfr_integrate; nothing waits for the host.
+ * scratch: n + 1 ints of device memory, scratch[n] = number of conditions handed over. */
+int pfr_stiff_fallback(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0, const float* tgrid,
+                       const float* Tprof, const float* t_end, const int* idx_end, double rtol, double atol, int max_steps, int flags,
+                       void* y_out, void* y_dense, int* status, int* stats, int* scratch, void* stream);
+
 /* ---- the whole sweep as one call ----------------------------------------------------------------------------------------
  * main() of SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:259-369 (temp_mlp NULL: isothermal sweep, T = T0, outlet at the
  * last knot of the (T, P, L, u0) time grid) and of ...Eon_single_model.py:279-354 (coupled sweep: temperature profile and
@@ -173,6 +185,9 @@ int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, co
                   const float* ref, const float* yscale, int substeps, double* loss, double* grad, void* stream);
 /* out[r] = sum_i x[r][i] with a fixed summation tree (deterministic reduction of per-condition gradients) */
 int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream);
+/* the same over the columns with status[i] == 0 only (conditions whose forward integration succeeded); out[rows] = their number.
+ * The training step reduces [grad(189) | loss] this way, so a failed trajectory enters neither the gradient nor the mean. */
+int pfr_reduce_rows_ok(const double* x, int rows, int n, const int* status, double* out, void* stream);
 
 /* Accuracy numbers of the reference's per-case / per-species CSV, all conditions at once
  * (...Eoff_single_model.py:384-480, ...Eon_single_model.py:381-463).

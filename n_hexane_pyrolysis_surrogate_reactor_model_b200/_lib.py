@@ -15,6 +15,7 @@ METHOD_RODAS4_TPC = 2
 METHOD_ROS3 = 3
 METHOD_BS23 = 4
 METHOD_DP54 = 5
+METHOD_BS23_WARP = 6
 ST_STIFF = 4
 SWEEP_NO_ORDER, SWEEP_NO_FALLBACK = 1, 2
 STATUS_TEXT = {0: "ok", 1: "max steps exceeded", 2: "non-finite state", 3: "step size underflow",
@@ -68,11 +69,16 @@ def _declare(lib):
     lib.pfr_integrate.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]
+    lib.pfr_stiff_fallback.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                       c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pfr_stiff_fallback.restype = c_int
     lib.pfr_loss_grad.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p]
     lib.pfr_loss_grad.restype = c_int
     lib.pfr_reduce_rows.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.pfr_reduce_rows.restype = c_int
+    lib.pfr_reduce_rows_ok.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pfr_reduce_rows_ok.restype = c_int
     lib.pfr_accuracy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.pfr_accuracy.restype = c_int
     fpp = ctypes.POINTER(c_float_p)

@@ -255,30 +255,41 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
         else { ia[s] = 11; ib[s] = 0; }
     }
 
-    const double wnorm = 1.0 / (double)(NOBS * NTOT);
+    const double wnorm = 1.0 / (double)(NOBS * NTOT), inv_sub = 1.0 / (double)a.substeps;
     const double T0 = (double)a.T0[i];
-    const double sc = (lane < NOBS) ? (double)a.yscale[(size_t)lane * n + i] : 1.0;
+    const double isc = (lane < NOBS) ? 1.0 / (double)a.yscale[(size_t)lane * n + i] : 1.0;
     double loss = 0.0, lam = 0.0;
 
     // node evaluation: forward quantities at (T, y) -> stored node `slot`; returns f_k, q_k, md_k, mz_k for this lane
     auto node = [&](int slot, double T, double y, double& f, double& q, double& md, double& mz) {
         const double Y = m_min(m_max(y, p.lb), p.ub);
-        double wvv = fast_log(lane == NS + 1 ? T : Y, ft.logtab);   // lanes 0..8: ln Y_k; lane 10: ln T
-        q = (y >= p.lb && y <= p.ub) ? 1.0 / Y : 0.0;
-        if (lane == NS) wvv = -p.inv_R / T;
+        double wvv = fast_log_ilp(lane == NS + 1 ? T : Y, ft.logtab);   // lanes 0..8: ln Y_k; lane 10: ln T
+        q = (y >= p.lb && y <= p.ub) ? rcp_full(Y) : 0.0;   // (an IEEE division is a ~20-deep dependent chain: a third of this kernel's time)
+        if (lane == NS) wvv = -p.inv_R * rcp_full(T);
         if (lane < NS + 2) S.V[slot][lane] = wvv;
         if (lane == NS + 2) S.V[slot][11] = 1.0;
         __syncwarp();
-        double z = lnA;
+        // three partial sums: the warp has no other warp to hide an 11-deep FMA chain behind
+        double z0 = lnA, z1 = 0.0, z2 = 0.0;
 #pragma unroll
-        for (int r = 0; r < NS + 2; r++) z = fma(win_col[r], S.V[slot][r], z);
-        const double rr = fast_exp(m_min(m_max(z, p.zlo), p.zhi), ft.exptab);
+        for (int r = 0; r < 4; r++) z0 = fma(win_col[r], S.V[slot][r], z0);
+#pragma unroll
+        for (int r = 4; r < 8; r++) z1 = fma(win_col[r], S.V[slot][r], z1);
+#pragma unroll
+        for (int r = 8; r < NS + 2; r++) z2 = fma(win_col[r], S.V[slot][r], z2);
+        const double z = (z0 + z1) + z2;
+        const double rr = fast_exp_ilp(m_min(m_max(z, p.zlo), p.zhi), ft.exptab);
         mz = (z >= p.zlo && z <= p.zhi) ? 1.0 : 0.0;
         if (sp) S.R[slot][lane] = rr;
         __syncwarp();
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NR; j++) s = fma(wout_row[j], S.R[slot][j], s);
+        for (int j = 0; j < 3; j++) {
+            s0 = fma(wout_row[j], S.R[slot][j], s0);
+            s1 = fma(wout_row[j + 3], S.R[slot][j + 3], s1);
+            s2 = fma(wout_row[j + 6], S.R[slot][j + 6], s2);
+        }
+        const double s = (s0 + s1) + s2;
         f = m_min(m_max(s, p.dulo), p.duhi);
         md = (s >= p.dulo && s <= p.duhi) ? 1.0 : 0.0;
     };
@@ -287,15 +298,24 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
         __syncwarp();
         if (sp) { S.V[slot][12 + lane] = l * md; S.U[9 + lane] = S.R[slot][lane]; }
         __syncwarp();
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int r = 0; r < NS; r++) s = fma(S.V[slot][12 + r], wout_col[r], s);
-        const double mu = s * S.R[slot][k] * mz;
+        for (int r = 0; r < 3; r++) {
+            s0 = fma(S.V[slot][12 + r], wout_col[r], s0);
+            s1 = fma(S.V[slot][15 + r], wout_col[r + 3], s1);
+            s2 = fma(S.V[slot][18 + r], wout_col[r + 6], s2);
+        }
+        const double mu = ((s0 + s1) + s2) * (S.R[slot][k] * mz);
         if (sp) S.U[lane] = mu;
         __syncwarp();
-        double jt = 0.0;
+        double j0 = 0.0, j1 = 0.0, j2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NR; j++) jt = fma(nu_row[j], S.U[j], jt);
+        for (int j = 0; j < 3; j++) {
+            j0 = fma(nu_row[j], S.U[j], j0);
+            j1 = fma(nu_row[j + 3], S.U[j + 3], j1);
+            j2 = fma(nu_row[j + 6], S.U[j + 6], j2);
+        }
+        const double jt = (j0 + j1) + j2;
 #pragma unroll
         for (int e = 0; e < 6; e++) G[e] = fma(w * S.V[slot][ia[e]], S.U[ib[e]], G[e]);
         return jt * q;
@@ -317,9 +337,9 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
         if (kk > 0 && lane < NOBS) ref_n = a.ref[((size_t)(kk - 1) * NOBS + lane) * n + i];
         if (lane < NOBS) {
             const double pc = m_min(m_max(yb, p.lb), p.ub);
-            const double d = (pc - (double)ref_c) / sc;
+            const double d = (pc - (double)ref_c) * isc;
             loss = fma(d, d, loss);
-            if (yb >= p.lb && yb <= p.ub) lam += 2.0 * d / sc * wnorm;
+            if (yb >= p.lb && yb <= p.ub) lam += 2.0 * d * isc * wnorm;
         }
         if (kk == 0) break;
         const double ta = (double)ta_n;
@@ -332,7 +352,7 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
         }
         double fa, qa, mda, mza;
         node(2, Ta, ya, fa, qa, mda, mza);  // lower end -> slot 2
-        const double h = tb - ta, slope = (Tb - Ta) / h, hs = h / (double)a.substeps;
+        const double h = tb - ta, ih = rcp_full(h), slope = (Tb - Ta) * ih, hs = h * inv_sub;
         // upper node of the current sub-step lives in slot 0 with (q1, md1, mz1)
         double q1 = qb, md1 = mdb, mz1 = mzb;
         for (int ss = 0; ss < a.substeps; ss++) {
@@ -343,7 +363,7 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
             double fm, qm, mdm, mzm;
             {
                 const double tau = tau1 - 0.5 * hs;
-                const double s = (tau - ta) / h, s2 = s * s, s3 = s2 * s;
+                const double s = (tau - ta) * ih, s2 = s * s, s3 = s2 * s;
                 const double ym = (2 * s3 - 3 * s2 + 1) * ya + (s3 - 2 * s2 + s) * h * fa + (-2 * s3 + 3 * s2) * yb + (s3 - s2) * h * fb;
                 __syncwarp();
                 node(1, kRamp ? Ta + slope * (tau - ta) : T0, ym, fm, qm, mdm, mzm);
@@ -355,7 +375,7 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
                 k4 = contract(2, fma(hs, k3, lam), qa, mda, mza, hs / 6.0);
             } else {
                 const double tau = tau1 - hs;
-                const double s = (tau - ta) / h, s2 = s * s, s3 = s2 * s;
+                const double s = (tau - ta) * ih, s2 = s * s, s3 = s2 * s;
                 const double y0 = (2 * s3 - 3 * s2 + 1) * ya + (s3 - 2 * s2 + s) * h * fa + (-2 * s3 + 3 * s2) * yb + (s3 - s2) * h * fb;
                 double f0;
                 __syncwarp();
@@ -382,12 +402,17 @@ adjoint_warp_kernel(const __grid_constant__ CrnnParams<double> p, const AdjointA
     }
 }
 
-// out[r] = sum_i x[r][i], fixed summation tree (deterministic): one block per row
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restrict__ x, int n, double* __restrict__ out) {
+// out[r] = sum_i x[r][i], fixed summation tree (deterministic): one block per row.  With `status` given only the columns with
+// status[i] == 0 are summed (a condition whose forward integration failed contributes neither loss nor gradient -- its row
+// entries may be NaN, so they are skipped, not multiplied by zero) and block `rows` writes their number to out[rows].
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restrict__ x, int n, int rows, const int* __restrict__ status,
+                                                          double* __restrict__ out) {
     __shared__ double sh[256];
+    const bool counting = (int)blockIdx.x == rows;
     const double* row = x + (size_t)blockIdx.x * n;
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) s += row[i];
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (!status || status[i] == 0) s += counting ? 1.0 : row[i];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int w = 128; w > 0; w >>= 1) {

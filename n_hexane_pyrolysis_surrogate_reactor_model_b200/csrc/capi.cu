@@ -17,6 +17,7 @@
 #include "integrate_explicit.cuh"
 #include "integrate_rodas_coop.cuh"
 #include "integrate_explicit.cuh"
+#include "integrate_lanes.cuh"
 #include "adjoint.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
@@ -684,6 +685,14 @@ static int integrate_launch(DeviceCtx& ctx, crnn_model_t m, int method, int prec
         case PFR_METHOD_ROS3: return d ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
         case PFR_METHOD_DP54: return d ? dispatch_dp54<double>(ctx, m->pd, a, st) : dispatch_dp54<float>(ctx, m->pf, a, st);
         case PFR_METHOD_BS23: return d ? dispatch_bs23<double>(ctx, m->pd, a, st) : dispatch_bs23<float>(ctx, m->pf, a, st);
+        case PFR_METHOD_BS23_WARP: {
+            if (!d) return PFR_EINVAL;
+            const int blocks = (a.n + LANES_WARPS - 1) / LANES_WARPS;
+            if (a.Tprof) bs23_lanes_kernel<true><<<blocks, 32 * LANES_WARPS, 0, st>>>(m->pd, a);
+            else bs23_lanes_kernel<false><<<blocks, 32 * LANES_WARPS, 0, st>>>(m->pd, a);
+            CK_LAUNCH("bs23_lanes_kernel");
+            return PFR_OK;
+        }
         case PFR_METHOD_RODAS4_TPC: return d ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
         case PFR_METHOD_DOPRI5: {
             Dopri5Args da{a.n, a.T0, a.c0, a.tgrid, a.Tprof, a.t_end, a.idx_end, a.perm, a.rtol, a.atol, a.y_out, a.y_dense, a.status, a.stats, a.max_steps};
@@ -699,7 +708,10 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (n == 0) return PFR_OK;
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
-    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 && method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54) return PFR_EINVAL;
+    if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 &&
+        method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54 && method != PFR_METHOD_BS23_WARP)
+        return PFR_EINVAL;
+    if (method == PFR_METHOD_BS23_WARP && (!tgrid || precision != 64)) return PFR_EINVAL;   // knot-limited, float64 state
     if (method == PFR_METHOD_DP54 && (tgrid || !t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;   // isothermal outlet at t_end only
     if (method == PFR_METHOD_BS23 && !tgrid) return PFR_EINVAL;   // the explicit fast path is the knot-limited stepper
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
@@ -715,6 +727,32 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     return integrate_launch(*ctx, m, method, precision, a, (cudaStream_t)stream);
 }
 
+
+// Second half of an explicit-fast-path integration, for callers that drive the stages themselves (Surrogate.integrate): the
+// conditions that pfr_integrate(PFR_METHOD_BS23 | PFR_METHOD_DP54) left with status PFR_ST_STIFF are collected into a list ON THE
+// DEVICE and integrated again, from the inlet, with the Rosenbrock kernel, which overwrites their y_out / y_dense / status / stats.
+// Nothing waits for the host; with no flagged condition the second launch finds an empty list and returns at once.
+// scratch: n + 1 ints of device memory; scratch[n] receives the number of conditions handed over.
+extern "C" int pfr_stiff_fallback(crnn_model_t m, int method, int precision, int n, const float* T0, const float* c0, const float* tgrid,
+                                  const float* Tprof, const float* t_end, const int* idx_end, double rtol, double atol, int max_steps,
+                                  int flags, void* y_out, void* y_dense, int* status, int* stats, int* scratch, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!m || !T0 || !c0 || !y_out || !status || !scratch || n < 0) return PFR_EINVAL;
+    if (method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4) return PFR_EINVAL;
+    if (precision != 32 && precision != 64) return PFR_EINVAL;
+    if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
+    if (max_steps <= 0) max_steps = 1000000;
+    DeviceCtx* ctx = nullptr;
+    int rc = device_ctx(&ctx);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(scratch + n, 0, sizeof(int), st));
+    collect_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(status, nullptr, n, PFR_ST_STIFF, scratch, scratch + n);
+    CK_LAUNCH("collect_status_kernel");
+    RodasArgs a{n, T0, c0, tgrid, Tprof, t_end, idx_end, scratch, rtol, atol, y_out, y_dense, status, stats, max_steps, ctx->tables, flags};
+    a.n_work = scratch + n;
+    return integrate_launch(*ctx, m, method, precision, a, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // The whole hot path of one model variant as ONE call (main() sweep loops of SURROGATE_MODEL/surrogate_model_Eoff_single_model.py:
@@ -973,7 +1011,14 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
 extern "C" int pfr_reduce_rows(const double* x, int rows, int n, double* out, void* stream) {
     if (rows == 0) return PFR_OK;
     if (!x || !out || rows < 0 || n < 0) return PFR_EINVAL;
-    reduce_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    reduce_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, n, rows, nullptr, out);
+    CK_LAUNCH("reduce_rows_kernel");
+    return PFR_OK;
+}
+
+extern "C" int pfr_reduce_rows_ok(const double* x, int rows, int n, const int* status, double* out, void* stream) {
+    if (!x || !out || !status || rows < 0 || n < 0) return PFR_EINVAL;
+    reduce_rows_kernel<<<rows + 1, 256, 0, (cudaStream_t)stream>>>(x, n, rows, status, out);
     CK_LAUNCH("reduce_rows_kernel");
     return PFR_OK;
 }

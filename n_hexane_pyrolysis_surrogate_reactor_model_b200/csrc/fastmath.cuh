@@ -70,4 +70,52 @@ __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ 
     return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
 }
 
+// 1/x to ~1e-10 (MUFU.RCP64H seed + one Newton step): enough for the weights of the error norm
+__device__ __forceinline__ double rcp_norm(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ float rcp_norm(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double rcp_full(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float rcp_full(float x) { return __frcp_rn(x); }
+
+// Latency-oriented variants for the kernels that run one warp per condition with no other warp to hide a dependent chain
+// behind (the training step: a few hundred conditions on 148 SMs).  Same tables, same range reduction, same polynomial; the
+// polynomial is evaluated Estrin-style (depth 4 instead of 6) and the two-term reconstruction is split so that the exponent part
+// does not wait for the polynomial.  Results differ from fast_log / fast_exp by rounding only (<= 1 ulp).
+__device__ __forceinline__ double fast_log_ilp(double x, const double2* __restrict__ tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = tab[(hi >> 13) & (LOGTAB_N - 1)];
+    const double ed = __hiloint2double(0x43300000, hi >> 20) - (4503599627370496.0 + 1023.0);
+    const double base = fma(ed, LN2_HI, t.y);                 // independent of the polynomial
+    const double r = fma(m, t.x, -1.0);
+    const double r2 = r * r;
+    const double a = fma(r, 1.0 / 3.0, -0.5), b = fma(r, 0.2, -0.25);
+    const double q = fma(r2, fma(r2, -1.0 / 6.0, b), a);      // -1/2 + r/3 + r^2 (-1/4 + r/5 - r^2/6)
+    return base + fma(ed, LN2_LO, fma(r2, q, r));
+}
+
+__device__ __forceinline__ double fast_exp_ilp(double x, const double* __restrict__ tab) {
+    const double sh = fma(x, 92.33248261689366, MAGIC_52_51);
+    const int k = __double2loint(sh);
+    const double kd = sh - MAGIC_52_51;
+    const double T = tab[k & (EXPTAB_N - 1)];
+    double r = fma(kd, -LN2_HI / 64.0, x);
+    r = fma(kd, -LN2_LO / 64.0, r);
+    const double r2 = r * r;
+    const double a = fma(r, 1.0 / 6.0, 0.5), b = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double q = fma(r2, fma(r2, 1.0 / 720.0, b), a);     // 1/2 + r/6 + r^2 (1/24 + r/120 + r^2/720)
+    const double res = fma(T, fma(r2, q, r), T);
+    return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+}
+
 }  // namespace pfr

@@ -58,23 +58,6 @@ template <typename real> __device__ __forceinline__ real t_exp(real x, const Fas
 template <> __device__ __forceinline__ double t_exp<double>(double x, const FastTables& ft) { return fast_exp(x, ft.exptab); }
 template <> __device__ __forceinline__ float t_exp<float>(float x, const FastTables&) { return expf(x); }
 
-// 1/x to ~1e-10 (MUFU.RCP64H seed + one Newton step): enough for the weights of the error norm
-__device__ __forceinline__ double rcp_norm(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return fma(r, fma(-x, r, 1.0), r);
-}
-__device__ __forceinline__ float rcp_norm(float x) { return __frcp_rn(x); }
-__device__ __forceinline__ double rcp_full(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ float rcp_full(float x) { return __frcp_rn(x); }
-
 // Block-shared copy of the CRNN coefficients, laid out in the order the right-hand side consumes them.  Every thread
 // reads the same address (a broadcast), two coefficients per 16-byte load.  (As FMA operands straight from the
 // constant bank they would have to pass through uniform registers on sm_100: 189 64-bit values do not fit, and the

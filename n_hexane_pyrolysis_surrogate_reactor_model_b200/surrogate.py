@@ -34,7 +34,7 @@ TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eo
 # sit at 1e-6 ... 1e-3 mol/m3 are governed by atol, everything else by rtol, so the two are set separately.
 FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-7)}
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
-           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54}
+           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP}
 
 
 def _ptr(t):
@@ -277,9 +277,16 @@ class Surrogate:
                                             _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
         res = SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
-        if method in ("bs23", "dp54") and stiff_fallback:
-            self._integrate_stiff_remainder(res, T0, c0, "rodas4" if method == "dp54" else stiff_fallback, precision, rtol, atol,
-                                            max_steps, dense_raw)
+        if method in ("bs23", "bs23w", "dp54") and stiff_fallback:
+            # The explicit fast paths stop a condition whose steps turn out stability-limited with PFR_ST_STIFF; those conditions
+            # (none for the shipped parameter sets) are integrated again, from the inlet, with the Rosenbrock kernel and their
+            # results written over the flagged entries.  List and count stay on the device (pfr_stiff_fallback): no host sync.
+            fb = "rodas4" if method == "dp54" else stiff_fallback
+            scratch = torch.empty(n + 1, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().pfr_stiff_fallback(self.crnn.handle, METHODS[fb], precision, n, _ptr(T0), _ptr(c0), _ptr(tgrid), _ptr(Tprof),
+                                                     _ptr(t_end), _ptr(idx_end), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y), _ptr(yd),
+                                                     _ptr(status), _ptr(stats), _ptr(scratch), _stream()), "pfr_stiff_fallback")
+            res.stiff = scratch[n:]
         return res
 
     def _check_integrate_args(self, n, c0, tgrid, Tprof, t_end, idx_end, perm):
@@ -297,27 +304,6 @@ class Surrogate:
         need("t_end", t_end, torch.float32, (n,))
         need("idx_end", idx_end, torch.int32, (n,))
         need("perm", perm, torch.int32, (n,))
-
-    def _integrate_stiff_remainder(self, res, T0, c0, method, precision, rtol, atol, max_steps, dense_raw):
-        """The explicit fast path (PFR_METHOD_BS23) stops a condition whose knot intervals turn out stiff with
-        PFR_ST_STIFF; those conditions (none for the shipped parameter sets) are integrated again, from the inlet, with
-        the Rosenbrock kernel and their results written over the flagged entries."""
-        stiff = res.status == _lib.ST_STIFF
-        if not bool(stiff.any()):
-            return
-        sel = stiff.nonzero().flatten()
-        sub = self.integrate(T0[sel], c0[sel], tgrid=None if res.tgrid is None else res.tgrid[:, sel].contiguous(),
-                             t_end=None if res.tgrid is not None or res.t_end is None else res.t_end[sel].contiguous(),
-                             Tprof=None if res.Tprof is None else res.Tprof[:, sel].contiguous(),
-                             idx_end=None if res.idx_cut is None else res.idx_cut[sel].contiguous(), method=method,
-                             precision=precision, rtol=rtol, atol=atol, dense=res.dense is not None, max_steps=max_steps,
-                             dense_raw=dense_raw)
-        res.y[:, sel] = sub.y
-        res.status[sel] = sub.status
-        res.stats[:, sel] += sub.stats
-        if res.dense is not None:
-            res.dense[:, :, sel] = sub.dense
-        res.stiff = int(sel.numel())
 
     # ------------------------------------------------------------------ the sweep (hot path)
     def _sweep_one_call(self, T, P, L, u0, method, precision, rtol, atol, integrator_events) -> SolveResult:

@@ -182,46 +182,85 @@ class CrnnTrainer:
         self._sur.energy_on = batch.Tprof is not None
         # forward integrator: every step ends on a knot of the label grid (dense output), i.e. the knot-limited regime in
         # which the explicit fast path is 2-4x cheaper than the Rosenbrock kernel (stiff conditions fall back to it)
-        self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "bs23")
+        # ("bs23w": that integrator with one condition per warp -- a training batch is a few hundred conditions, so the pass is
+        # latency-bound and nine lanes per right-hand side make it ~4x shorter than one thread per condition, "bs23")
+        self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "bs23w")
+        self._crnn, self._bufs, self.failed_last = None, {}, 0
 
     # ---------------------------------------------------------------- device part
+    def _model(self, w_in, w_b, w_out) -> CrnnModel:
+        """ONE model handle for the trainer's lifetime: the parameters of a step are written into it (crnn_model_update; they reach
+        the kernels by value at launch), instead of a handle created and destroyed per step."""
+        params = CRNNParams(w_in, w_b, w_out)
+        if self._crnn is None:
+            self._crnn = CrnnModel(params, self.clamps)
+        else:
+            self._crnn.update(params)
+        self._sur.crnn = self._crnn
+        return self._crnn
+
     def forward(self, w_in, w_b, w_out, batch: TrainingBatch | None = None):
         """Raw knot states [801, 9, n] (float64) of the current parameters; status [n]."""
-        crnn = CrnnModel(CRNNParams(w_in, w_b, w_out), self.clamps)
-        self._sur.crnn = crnn
+        crnn = self._model(w_in, w_b, w_out)
         b = batch or self.batch
         res = self._sur.integrate(b.T0, b.c0, tgrid=b.tgrid, Tprof=b.Tprof, rtol=self.rtol, atol=self.atol, dense=True, dense_raw=True,
                                   method=self.forward_method)
         return crnn, res
 
-    def loss_grad_w(self, w_in, w_b, w_out, batch: TrainingBatch | None = None):
-        """(sum of per-condition losses, sum of per-condition gradients [189], failed count) on this rank, float64 CUDA."""
+    def _buffers(self, n: int):
+        """[grad(189) | loss] x n per-condition rows, the packed [grad | loss | count] vector and its page-locked host copy, kept
+        per batch size so that a step allocates nothing but the forward pass's own outputs."""
+        buf = self._bufs.get(n)
+        if buf is None:
+            buf = self._bufs[n] = (torch.empty((NPAR + 1, n), dtype=torch.float64, device=self.device),
+                                   torch.empty(NPAR + 3, dtype=torch.float64, device=self.device),
+                                   torch.empty(NPAR + 3, dtype=torch.float64).pin_memory())
+        return buf
+
+    def packed_loss_grad(self, w_in, w_b, w_out, batch: TrainingBatch | None = None) -> torch.Tensor:
+        """This rank's [sum of gradients (189) | sum of losses | number of conditions summed | number of conditions attempted],
+        float64 on the device (the vector the step all-reduces); the sums run over the conditions whose forward integration
+        succeeded."""
         b = batch or self.batch
         crnn, res = self.forward(w_in, w_b, w_out, b)
         n = b.n
-        loss = torch.empty(n, dtype=torch.float64, device=self.device)
-        grad = torch.empty((NPAR, n), dtype=torch.float64, device=self.device)
+        rows, packed, _ = self._buffers(n)
         _lib.check(_lib.lib().pfr_loss_grad(crnn.handle, n, _ptr(b.T0), _ptr(b.tgrid), _ptr(b.Tprof), _ptr(res.dense), _ptr(b.ref),
-                                            _ptr(b.yscale), self.substeps, _ptr(loss), _ptr(grad), _stream()), "pfr_loss_grad")
-        out = torch.empty(NPAR + 1, dtype=torch.float64, device=self.device)
-        both = torch.cat([grad, loss.unsqueeze(0)], dim=0).contiguous()
-        _lib.check(_lib.lib().pfr_reduce_rows(_ptr(both), NPAR + 1, n, _ptr(out), _stream()), "pfr_reduce_rows")
-        return out[NPAR], out[:NPAR], int((res.status != 0).sum())
+                                            _ptr(b.yscale), self.substeps, _ptr(rows[NPAR]), _ptr(rows), _stream()), "pfr_loss_grad")
+        # a failed trajectory (status != 0) enters neither the sums nor the count
+        _lib.check(_lib.lib().pfr_reduce_rows_ok(_ptr(rows), NPAR + 1, n, _ptr(res.status), _ptr(packed), _stream()), "pfr_reduce_rows_ok")
+        packed[NPAR + 2:].fill_(float(n))
+        return packed
+
+    def loss_grad_w(self, w_in, w_b, w_out, batch: TrainingBatch | None = None):
+        """(sum of per-condition losses, sum of per-condition gradients [189], failed count) on this rank, float64 CUDA."""
+        b = batch or self.batch
+        packed = self.packed_loss_grad(w_in, w_b, w_out, b).clone()
+        return packed[NPAR], packed[:NPAR], int(round(float(packed[NPAR + 2] - packed[NPAR + 1])))
+
+    def _reduce_to_host(self, packed: torch.Tensor, n: int) -> torch.Tensor:
+        """All-reduce the packed vector over the ranks and bring it to the host: one collective, one page-locked copy, one wait."""
+        packed = allreduce_packed(packed, self.group)
+        host = self._buffers(n)[2]
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
 
     # ---------------------------------------------------------------- host part (189 numbers)
     def loss_and_grad(self, p: torch.Tensor, idx=None):
-        """Mean loss over all ranks' conditions (or over this rank's conditions `idx`, a mini-batch) and its gradient
-        with respect to p (float32 CPU tensors)."""
+        """Mean loss over all ranks' (successfully integrated) conditions -- or over this rank's conditions `idx`, a mini-batch --
+        and its gradient with respect to p (float32 CPU tensors); third value: failed trajectories (all ranks), which entered
+        neither the mean nor the gradient."""
         b = self.batch if idx is None else self.batch.subset(idx)
         pc = p.detach().to("cpu", torch.float32).requires_grad_(True)
         w_in, w_b, w_out = self.converter(pc)
-        lsum, gsum, bad = self.loss_grad_w(w_in.detach().numpy(), w_b.detach().numpy(), w_out.detach().numpy(), b)
-        packed = torch.cat([gsum, lsum.reshape(1), torch.tensor([float(b.n)], dtype=torch.float64, device=self.device)])
-        packed = allreduce_packed(packed, self.group).cpu()
-        count = float(packed[NPAR + 1])
+        packed = self._reduce_to_host(self.packed_loss_grad(w_in.detach().numpy(), w_b.detach().numpy(), w_out.detach().numpy(), b), b.n)
+        count = max(float(packed[NPAR + 1]), 1.0)
+        bad = int(round(float(packed[NPAR + 2] - packed[NPAR + 1])))   # failed trajectories, all ranks
         g = (packed[:NPAR] / count).to(torch.float32)
         g_in, g_b, g_out = g[:99].view(11, 9), g[99:108], g[108:].view(9, 9)
         (gp,) = torch.autograd.grad((w_in, w_b, w_out), pc, (g_in, g_b, g_out))
+        self.failed_last = bad
         return float(packed[NPAR]) / count, gp, bad
 
     def loss(self, p: torch.Tensor, idx=None) -> float:
@@ -229,11 +268,8 @@ class CrnnTrainer:
         b = self.batch if idx is None else self.batch.subset(idx)
         with torch.no_grad():
             w_in, w_b, w_out = self.converter(p.detach().to("cpu", torch.float32))
-        lsum, _, _ = self.loss_grad_w(w_in.numpy(), w_b.numpy(), w_out.numpy(), b)
-        packed = torch.zeros(NPAR + 2, dtype=torch.float64, device=self.device)
-        packed[NPAR], packed[NPAR + 1] = lsum, float(b.n)
-        packed = allreduce_packed(packed, self.group).cpu()
-        return float(packed[NPAR]) / float(packed[NPAR + 1])
+        packed = self._reduce_to_host(self.packed_loss_grad(w_in.numpy(), w_b.numpy(), w_out.numpy(), b), b.n)
+        return float(packed[NPAR]) / max(float(packed[NPAR + 1]), 1.0)
 
     def step(self, p: torch.Tensor, idx=None):
         """One optimiser step on p (a CPU float32 leaf tensor): gradient over the whole batch (or the mini-batch `idx`),
@@ -273,16 +309,19 @@ def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrai
                       (random.shuffle(train_idx), one optimiser step per sample, train loss = mean of the per-step losses).
     With several ranks every rank must hold the same number of conditions so that the step counts agree."""
     history = {"train_loss": [], "valid_loss": [], "parameters": []}
+    failed_total = 0
     sched = None
     if lr_factor is None:
         lr_factor = trainer.settings.lr_factor if trainer.settings is not None else 0.8
     rng = np.random.default_rng(shuffle_seed)
     for epoch in range(epochs):
         if batch_size is None:
-            losses = [trainer.step(p)[0] for _ in range(steps_per_epoch)]
+            out = [trainer.step(p) for _ in range(steps_per_epoch)]
+            losses, failed_total = [o[0] for o in out], failed_total + sum(o[1] for o in out)
         else:
             order = np.arange(trainer.batch.n) if shuffle_seed is None else rng.permutation(trainer.batch.n)
-            losses = [trainer.step(p, order[s:s + batch_size])[0] for s in range(0, len(order), batch_size)]
+            out = [trainer.step(p, order[s:s + batch_size]) for s in range(0, len(order), batch_size)]
+            losses, failed_total = [o[0] for o in out], failed_total + sum(o[1] for o in out)
         if sched is None:
             sched = torch.optim.lr_scheduler.ReduceLROnPlateau(trainer.opt, mode="min", factor=lr_factor, patience=5, threshold=1e-4,
                                                                threshold_mode="rel")
@@ -292,6 +331,8 @@ def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrai
         history["valid_loss"].append(float(vloss))
         w_in, w_b, w_out = (x.detach().cpu().numpy() for x in trainer.converter(p.detach()))
         history["parameters"].append({"w_in": w_in, "w_b": w_b, "w_out": w_out})
+        if failed_total and log:
+            log(epoch, f"{failed_total} forward trajectories failed so far; they were left out of the loss and the gradient", vloss, None)
         if log:
             log(epoch, history["train_loss"][-1], vloss, trainer.opt.param_groups[0]["lr"])
         if save_path:
@@ -299,6 +340,7 @@ def train(trainer: "CrnnTrainer", p: torch.Tensor, epochs: int, valid: "CrnnTrai
     if save_path:
         w = tuple(x.detach().cpu().numpy() for x in trainer.converter(p.detach()))
         save_history(save_path, history, final=w, p=p)
+    history["failed_trajectories"] = failed_total   # (after the last save: the reference's history files hold the three keys above only)
     return history
 
 

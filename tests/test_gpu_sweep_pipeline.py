@@ -92,3 +92,29 @@ def test_handles_refuse_a_foreign_device(surrogates):
     with torch.cuda.device(1):
         with pytest.raises(_lib.PfrError):
             s.time_grid(torch.as_tensor(T, device="cuda:1"), torch.as_tensor(P, device="cuda:1"))
+
+
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_warp_per_condition_bs23_equals_thread_per_condition(surrogates, golden, conditions, variant):
+    """PFR_METHOD_BS23_WARP (lane = species, the training step's forward pass) against PFR_METHOD_BS23: the same method and
+    controller with the dot products summed in another order -- identical step sequences, dense knot states and outlets equal to
+    1e-11 of the state's scale; degenerate outlet knots (idx_end = 0) and ragged batch sizes included."""
+    s = surrogates("LLNL", variant)
+    T, P, L, U = cond4(conditions)
+    ref = s.sweep(T, P, L, U, method="rodas4", keep_grids=True)      # for the grids
+    c0 = s.inlet_concentration(T, P)
+    idx = ref.idx_cut.clone() if variant == "Eon" else torch.full((len(T),), 800, dtype=torch.int32, device="cuda")
+    idx[::7] = 0
+    kw = dict(tgrid=ref.tgrid, Tprof=ref.Tprof, idx_end=idx, rtol=1e-8, atol=1e-10, dense=True, dense_raw=True)
+    a = s.integrate(T, c0, method="bs23", **kw)
+    b = s.integrate(T, c0, method="bs23w", **kw)
+    assert int(a.status.abs().sum()) == 0 and int(b.status.abs().sum()) == 0
+    assert torch.equal(a.stats[:2], b.stats[:2])                     # accepted / rejected steps
+    assert torch.equal(b.stats[2], 3 * (b.stats[0] + b.stats[1]) + (idx != 0).int())
+    scale = a.dense.abs().amax(dim=(0, 2), keepdim=True).clamp(min=1e-3)
+    assert float(((a.dense - b.dense).abs() / scale).max()) < 1e-11
+    assert float(((a.y - b.y).abs() / a.y.abs().clamp(min=1e-3)).max()) < 1e-11
+    for m in (1, 3, 5):
+        sub = s.integrate(T[:m], c0[:m], method="bs23w", tgrid=ref.tgrid[:, :m].contiguous(), Tprof=None if ref.Tprof is None else ref.Tprof[:, :m].contiguous(),
+                          idx_end=idx[:m].contiguous(), rtol=1e-8, atol=1e-10)
+        assert torch.equal(sub.y, b.y[:, :m])

@@ -284,3 +284,50 @@ def test_minibatch_schedule_and_eon_training_loop(surrogates, model_sets, condit
         assert h["valid_loss"][-1] < first, (bs, first, h["valid_loss"])
         z = np.load(path, allow_pickle=True)
         assert len(z["train_loss"]) == 3 and z["parameters"][-1]["w_out"].shape == (9, 9) and z["updated_p"].shape == (189,)
+
+
+# ----------------------------------------------------------------------------------------------- two GPUs, NCCL
+def _nccl_worker(rank, world, port, ret):
+    """Each rank: its contiguous half of the 12-condition batch -> packed [grad | loss | ok | attempted] -> NCCL all-reduce."""
+    import torch.distributed as dist
+    from conftest import GOLDEN, packed_path
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.containers import ModelSet
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import Surrogate
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.sweep import shard_bounds
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import CrnnTrainer, allreduce_packed, synthetic_labels
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    a = np.load(os.path.join(GOLDEN, "conditions.npz"))["training_wide_2D"]
+    sel = np.linspace(0, len(a) - 1, 12).astype(int)
+    lo, hi = shard_bounds(len(sel), world, rank)
+    T, P = a[sel[lo:hi], 0].astype(np.float32), (a[sel[lo:hi], 1] * 1e5).astype(np.float32)
+    sur = Surrogate(ModelSet.from_packed(packed_path("LLNL"), "Eoff"), device=f"cuda:{rank}")
+    teacher = ModelSet.from_packed(packed_path("LLNL"), "Eoff", "Eoff_wide").crnn
+    student = ModelSet.from_packed(packed_path("LLNL"), "Eoff").crnn
+    tr = CrnnTrainer(synthetic_labels(sur, teacher, T, P))
+    packed = allreduce_packed(tr.packed_loss_grad(student.w_in, student.w_b, student.w_out))
+    ret[rank] = packed.cpu().numpy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_gradient_allreduce_equals_single_gpu(surrogates, model_sets, conditions):
+    """The training step's only collective on real hardware: two ranks, each with half of the batch, all-reduce their packed
+    vectors over NCCL; the result must equal the single-GPU reduction over the whole batch (both sum the same per-condition rows in
+    float64; the summation trees differ, hence 1e-12 relative to the vector's scale instead of bit equality)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    tr, batch, T, P = _setup(surrogates, model_sets, conditions)
+    student = model_sets("LLNL", "Eoff").crnn
+    single = tr.packed_loss_grad(student.w_in, student.w_b, student.w_out).cpu().numpy()
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    scale = np.abs(single[:189]).max()
+    for r in range(2):
+        assert np.max(np.abs(ret[r][:189] - single[:189])) <= 1e-12 * scale, r
+        assert abs(ret[r][189] - single[189]) <= 1e-12 * abs(single[189])
+        assert ret[r][190] == single[190] == 12.0 and ret[r][191] == 12.0
+    assert np.array_equal(ret[0], ret[1])

@@ -28,9 +28,19 @@ def main():
     # split: forward vs adjoint
     w = [x.detach().numpy() for x in tr.converter(p.detach())]
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    e[0].record(); crnn, res = tr.forward(*w); e[1].record(); tr.loss_grad_w(*w); e[2].record(); torch.cuda.synchronize()
+    e[0].record(); crnn, res = tr.forward(*w); e[1].record(); tr.packed_loss_grad(*w); e[2].record(); torch.cuda.synchronize()
+    # host-side share: the step without waiting for the device work of the previous one
+    t0 = time.time()
+    for _ in range(K):
+        pc = p.detach().to("cpu", torch.float32).requires_grad_(True)
+        w_in, w_b, w_out = tr.converter(pc)
+        (gp,) = torch.autograd.grad((w_in, w_b, w_out), pc, (torch.ones(11, 9), torch.ones(9), torch.ones(9, 9)))
+    host_conv = (time.time() - t0) / K
+    st = res.stats.double()
     print(json.dumps({"n": n, "step_ms": dt * 1e3, "samples_per_s": n / dt, "forward_ms": e[0].elapsed_time(e[1]),
-                      "forward_plus_adjoint_ms": e[1].elapsed_time(e[2]), "losses": losses[:3] + losses[-2:]}))
+                      "forward_plus_adjoint_ms": e[1].elapsed_time(e[2]), "converter_fwd_bwd_host_ms": host_conv * 1e3,
+                      "forward_attempts_mean": float((st[0] + st[1]).mean()), "forward_attempts_max": float((st[0] + st[1]).max()),
+                      "forward_method": tr.forward_method, "losses": losses[:3] + losses[-2:]}))
 
 if __name__ == "__main__":
     main()
