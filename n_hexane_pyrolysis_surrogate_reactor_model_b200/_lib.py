@@ -75,6 +75,11 @@ def _declare(lib):
     lib.pfr_loss_grad.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p]
     lib.pfr_loss_grad.restype = c_int
+    lib.pfr_loss_grad_workspace_bytes.argtypes = [c_int, c_int]
+    lib.pfr_loss_grad_workspace_bytes.restype = c_size_t
+    lib.pfr_loss_grad_staged.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.pfr_loss_grad_staged.restype = c_int
     lib.pfr_reduce_rows.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.pfr_reduce_rows.restype = c_int
     lib.pfr_reduce_rows_ok.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]

@@ -19,6 +19,7 @@
 #include "integrate_explicit.cuh"
 #include "integrate_lanes.cuh"
 #include "adjoint.cuh"
+#include "adjoint_phases.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_train.cuh"
@@ -1005,6 +1006,40 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
         else adjoint_kernel<false><<<blocks, ADJ_BLOCK, 0, (cudaStream_t)stream>>>(m->pd, a);
     }
     CK_LAUNCH("adjoint_kernel");
+    return PFR_OK;
+}
+
+// The same loss and gradient in three kernels (adjoint_phases.cuh): node quantities for all conditions x intervals at once, the
+// sequential adjoint walk reduced to one 9 x 9 mat-vec per stage, the parameter-gradient quadrature in parallel.
+extern "C" size_t pfr_loss_grad_workspace_bytes(int n, int substeps) {
+    if (n < 1 || substeps < 1) return 0;
+    return ((size_t)adj_nodes_per_condition(substeps) * ADJ_NF + (size_t)adj_stages_per_condition(substeps) * NS) * (size_t)n * sizeof(double);
+}
+
+extern "C" int pfr_loss_grad_staged(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof, const double* y_knots,
+                                    const float* ref, const float* yscale, int substeps, double* loss, double* grad, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (n == 0) return PFR_OK;
+    if (!m || !T0 || !tgrid || !y_knots || !ref || !yscale || !loss || !grad || !workspace || n < 0 || substeps < 1) return PFR_EINVAL;
+    if (workspace_bytes < pfr_loss_grad_workspace_bytes(n, substeps)) return PFR_EWORKSPACE;
+    DeviceCtx* ctx = nullptr;
+    {
+        const int rc = device_ctx(&ctx);
+        if (rc != PFR_OK) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    AdjPhaseArgs g;
+    g.a = AdjointArgs{n, T0, tgrid, Tprof, y_knots, ref, yscale, substeps, loss, grad, ctx->tables};
+    g.nodes = static_cast<double*>(workspace);
+    g.stages = g.nodes + (size_t)adj_nodes_per_condition(substeps) * ADJ_NF * (size_t)n;
+    const dim3 grid1((unsigned)((n + ADJP_BLOCK - 1) / ADJP_BLOCK), (unsigned)(NTOT - 1));
+    if (Tprof) adjoint_nodes_kernel<true><<<grid1, ADJP_BLOCK, 0, st>>>(m->pd, g);
+    else adjoint_nodes_kernel<false><<<grid1, ADJP_BLOCK, 0, st>>>(m->pd, g);
+    CK_LAUNCH("adjoint_nodes_kernel");
+    adjoint_sweep_kernel<<<(unsigned)((n + ADJS_WARPS - 1) / ADJS_WARPS), 32 * ADJS_WARPS, 0, st>>>(m->pd, g);
+    CK_LAUNCH("adjoint_sweep_kernel");
+    adjoint_grad_kernel<<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g);
+    CK_LAUNCH("adjoint_grad_kernel");
     return PFR_OK;
 }
 

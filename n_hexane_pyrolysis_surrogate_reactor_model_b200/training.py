@@ -186,6 +186,10 @@ class CrnnTrainer:
         # latency-bound and nine lanes per right-hand side make it ~4x shorter than one thread per condition, "bs23")
         self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "bs23w")
         self._crnn, self._bufs, self.failed_last = None, {}, 0
+        # gradient kernels: "staged" = three kernels with a workspace of 3.5 MB per condition (pfr_loss_grad_staged), "warp" = the
+        # single kernel, one condition per warp, no workspace (pfr_loss_grad); "auto" = staged while the workspace stays under 8 GB
+        self.adjoint = os.environ.get("PFR_TRAIN_ADJOINT", "auto")
+        self._adj_ws = None
 
     # ---------------------------------------------------------------- device part
     def _model(self, w_in, w_b, w_out) -> CrnnModel:
@@ -225,8 +229,17 @@ class CrnnTrainer:
         crnn, res = self.forward(w_in, w_b, w_out, b)
         n = b.n
         rows, packed, _ = self._buffers(n)
-        _lib.check(_lib.lib().pfr_loss_grad(crnn.handle, n, _ptr(b.T0), _ptr(b.tgrid), _ptr(b.Tprof), _ptr(res.dense), _ptr(b.ref),
-                                            _ptr(b.yscale), self.substeps, _ptr(rows[NPAR]), _ptr(rows), _stream()), "pfr_loss_grad")
+        need = _lib.lib().pfr_loss_grad_workspace_bytes(n, self.substeps) if self.substeps > 0 else 0
+        if need and (self.adjoint == "staged" or (self.adjoint == "auto" and need <= 8 << 30)):
+            if self._adj_ws is None or self._adj_ws.numel() < need:
+                self._adj_ws = None   # release the smaller one first
+                self._adj_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(_lib.lib().pfr_loss_grad_staged(crnn.handle, n, _ptr(b.T0), _ptr(b.tgrid), _ptr(b.Tprof), _ptr(res.dense), _ptr(b.ref),
+                                                       _ptr(b.yscale), self.substeps, _ptr(rows[NPAR]), _ptr(rows), _ptr(self._adj_ws),
+                                                       self._adj_ws.numel(), _stream()), "pfr_loss_grad_staged")
+        else:
+            _lib.check(_lib.lib().pfr_loss_grad(crnn.handle, n, _ptr(b.T0), _ptr(b.tgrid), _ptr(b.Tprof), _ptr(res.dense), _ptr(b.ref),
+                                                _ptr(b.yscale), self.substeps, _ptr(rows[NPAR]), _ptr(rows), _stream()), "pfr_loss_grad")
         # a failed trajectory (status != 0) enters neither the sums nor the count
         _lib.check(_lib.lib().pfr_reduce_rows_ok(_ptr(rows), NPAR + 1, n, _ptr(res.status), _ptr(packed), _stream()), "pfr_reduce_rows_ok")
         packed[NPAR + 2:].fill_(float(n))

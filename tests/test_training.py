@@ -139,16 +139,27 @@ def test_loss_and_gradient_vs_oracle_finite_differences(surrogates, model_sets, 
 
 
 @pytest.mark.gpu
-def test_warp_and_thread_adjoint_kernels_agree(surrogates, model_sets, conditions):
-    """The one-condition-per-warp adjoint kernel (product) against the one-condition-per-thread one (same arithmetic,
-    different mapping and summation order): losses and all 189 gradient entries agree to 1e-10 of the gradient scale."""
-    tr, batch, T, P = _setup(surrogates, model_sets, conditions, n=9)
-    student = model_sets("LLNL", "Eoff").crnn
-    l1, g1, _ = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
-    tr.substeps = -2
-    l2, g2, _ = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
-    assert abs(float(l1) - float(l2)) < 1e-12 * abs(float(l2))
-    assert float((g1 - g2).abs().max()) < 1e-10 * float(g2.abs().max())
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_three_adjoint_implementations_agree(surrogates, model_sets, conditions, variant):
+    """The three-kernel adjoint (product: node matrices in parallel, sequential walk of 9 x 9 mat-vecs, parallel gradient
+    quadrature), the one-condition-per-warp kernel and the one-condition-per-thread kernel are the same discretisation with
+    different mappings and summation orders: losses agree to 1e-12, all 189 gradient entries to 1e-10 of the gradient scale --
+    isothermal (wide trainer) and along a temperature ramp (narrow Eon trainer), ragged batch size."""
+    if variant == "Eoff":
+        tr, batch, T, P = _setup(surrogates, model_sets, conditions, n=9)
+        student = model_sets("LLNL", "Eoff").crnn
+    else:
+        tr, batch, T, P = _setup_eon(surrogates, model_sets, conditions, n=7)
+        student = model_sets("JetSurf", "Eon").crnn
+    out = {}
+    for name, adjoint, sub in (("staged", "staged", 2), ("warp", "warp", 2), ("thread", "warp", -2), ("staged3", "staged", 3), ("warp3", "warp", 3)):
+        tr.adjoint, tr.substeps = adjoint, sub
+        l, g, bad = tr.loss_grad_w(student.w_in, student.w_b, student.w_out)
+        assert bad == 0
+        out[name] = (float(l), g.clone())
+    for a, b in (("staged", "warp"), ("warp", "thread"), ("staged3", "warp3")):
+        assert abs(out[a][0] - out[b][0]) < 1e-12 * abs(out[b][0]), (a, b)
+        assert float((out[a][1] - out[b][1]).abs().max()) < 1e-10 * float(out[b][1].abs().max()), (a, b)
 
 
 @pytest.mark.gpu
