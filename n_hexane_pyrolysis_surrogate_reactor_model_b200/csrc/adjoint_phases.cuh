@@ -23,8 +23,12 @@
 
 namespace pfr {
 
-constexpr int ADJ_NF = 119;            // doubles per node record: M[9][9] | wv[11] | g[9] = r [z unclamped] | r[9] | md[9]
-constexpr int ADJ_F_M = 0, ADJ_F_WV = 81, ADJ_F_G = 92, ADJ_F_R = 101, ADJ_F_MD = 110;
+// Node record, 128 doubles per condition:
+//   M part   [row k = 0..8][condition][10]   row k of M = J^T padded to 10 doubles: a lane of the adjoint walk fetches its row as five
+//                                            16-byte copies, and a warp of the node kernel stores 32 adjacent rows contiguously
+//   vectors  [field = 0..37][condition]      wv[11] | g[9] = r [z unclamped] | r[9] | md[9]
+constexpr int ADJ_MROW = 10, ADJ_NV = 38, ADJ_NF = NS * ADJ_MROW + ADJ_NV;
+constexpr int ADJ_F_WV = 0, ADJ_F_G = 11, ADJ_F_R = 20, ADJ_F_MD = 29;
 constexpr int ADJP_BLOCK = 128;
 
 // nodes per condition: the 801 knots, then for every interval kk = 1..800 its 2 S - 1 interior nodes at tb - (j + 1) hs / 2
@@ -34,14 +38,17 @@ __host__ __device__ inline size_t adj_stages_per_condition(int S) { return (size
 
 struct AdjPhaseArgs {
     AdjointArgs a;
-    double* nodes;    // [nodes_per_condition][ADJ_NF][n]
+    double* nodes;    // [nodes_per_condition] records of ADJ_NF * n doubles: M part, then vectors (layout above)
     double* stages;   // [n][stages_per_condition][9]: lam at every RK4 stage, stage index ((kk - 1) S + ss) 4 + st
 };
+
+__host__ __device__ inline size_t adj_m_offset(size_t node, int k, size_t i, size_t n) { return (node * ADJ_NF + (size_t)k * ADJ_MROW) * n + i * ADJ_MROW; }
+__host__ __device__ inline size_t adj_v_offset(size_t node, int field, size_t i, size_t n) { return (node * ADJ_NF + (size_t)NS * ADJ_MROW + field) * n + i; }
 
 // ---------------------------------------------------------------------------------------------------------------- phase 1
 // forward quantities + M = J^T at (T, y); the record is stored unless rec == nullptr; returns f
 __device__ __forceinline__ void adj_node_full(const CrnnParams<double>& p, const FastTables& ft, double T, const double (&y)[NS],
-                                              double* __restrict__ rec, size_t n, double (&f)[NS]) {
+                                              double* __restrict__ nodes, long long node, size_t i, size_t n, double (&f)[NS]) {
     double wv[NS + 2], q[NS], g[NR], r[NR], md[NS];
 #pragma unroll
     for (int k = 0; k < NS; k++) {
@@ -67,15 +74,16 @@ __device__ __forceinline__ void adj_node_full(const CrnnParams<double>& p, const
         f[i] = m_min(m_max(s, p.dulo), p.duhi);
         md[i] = (s >= p.dulo && s <= p.duhi) ? 1.0 : 0.0;
     }
-    if (rec == nullptr) return;
+    if (node < 0) return;
     // (the vectors that only phase 3 needs leave first, so that their registers are free while M is assembled)
+    double* __restrict__ rv = nodes + adj_v_offset((size_t)node, 0, i, n);
 #pragma unroll
-    for (int e = 0; e < NS + 2; e++) rec[(size_t)(ADJ_F_WV + e) * n] = wv[e];
+    for (int e = 0; e < NS + 2; e++) rv[(size_t)(ADJ_F_WV + e) * n] = wv[e];
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-        rec[(size_t)(ADJ_F_G + j) * n] = g[j];
-        rec[(size_t)(ADJ_F_R + j) * n] = r[j];
-        rec[(size_t)(ADJ_F_MD + j) * n] = md[j];
+        rv[(size_t)(ADJ_F_G + j) * n] = g[j];
+        rv[(size_t)(ADJ_F_R + j) * n] = r[j];
+        rv[(size_t)(ADJ_F_MD + j) * n] = md[j];
     }
     // M[k][i] = q_k md_i sum_j nu[k][j] g_j wout[i][j]   ((J^T lam)_k = sum_i M[k][i] lam_i)
 #pragma unroll
@@ -83,13 +91,18 @@ __device__ __forceinline__ void adj_node_full(const CrnnParams<double>& p, const
         double aj[NR];
 #pragma unroll
         for (int j = 0; j < NR; j++) aj[j] = p.nu[k][j] * g[j];
+        double row[ADJ_MROW];
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
+        for (int c = 0; c < NS; c++) {
             double m = 0.0;
 #pragma unroll
-            for (int j = 0; j < NR; j++) m = fma(aj[j], p.wout[i][j], m);
-            rec[(size_t)(ADJ_F_M + k * NS + i) * n] = q[k] * md[i] * m;
+            for (int j = 0; j < NR; j++) m = fma(aj[j], p.wout[c][j], m);
+            row[c] = q[k] * md[c] * m;
         }
+        row[NS] = 0.0;
+        double2* __restrict__ dst = reinterpret_cast<double2*>(nodes + adj_m_offset((size_t)node, k, i, n));   // 80-byte rows: 16-byte aligned
+#pragma unroll
+        for (int c = 0; c < ADJ_MROW / 2; c++) dst[c] = make_double2(row[2 * c], row[2 * c + 1]);
     }
 }
 
@@ -128,15 +141,15 @@ adjoint_nodes_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
 #pragma unroll 1
     for (int j = -2; j < 2 * S - 1; j++) {
         double Tn;
-        double* rec;
+        long long node;   // < 0: no record
         if (j == -2) {
             Tn = Tb;
-            rec = g.nodes + (size_t)kk * ADJ_NF * n + i;
+            node = kk;
 #pragma unroll
             for (int k = 0; k < NS; k++) ym[k] = HV(yb, k);
         } else if (j == -1) {
             Tn = Ta;
-            rec = kk == 1 ? g.nodes + i : nullptr;
+            node = kk == 1 ? 0 : -1;
 #pragma unroll
             for (int k = 0; k < NS; k++) ym[k] = HV(ya, k);
         } else {
@@ -146,9 +159,9 @@ adjoint_nodes_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
 #pragma unroll
             for (int k = 0; k < NS; k++) ym[k] = ca * HV(ya, k) + cfa * HV(fa, k) + cb * HV(yb, k) + cfb * HV(fb, k);
             Tn = kRamp ? Ta + slope * (tau - ta) : T0;
-            rec = g.nodes + adj_interior_node(kk, j, S) * ADJ_NF * n + i;
+            node = (long long)adj_interior_node(kk, j, S);
         }
-        adj_node_full(p, ft, Tn, ym, rec, n, fm);
+        adj_node_full(p, ft, Tn, ym, g.nodes, node, (size_t)i, n, fm);
         if (j == -2) {
 #pragma unroll
             for (int k = 0; k < NS; k++) HV(fb, k) = fm[k];
@@ -167,15 +180,15 @@ constexpr int ADJS_DEPTH = 8;    // sub-steps whose matrices are in flight: the 
                                  // are copied into a shared-memory ring eight sub-steps ahead (cp.async, 8 bytes per copy; each
                                  // lane copies and later reads its own row, so no synchronisation beyond wait_group is needed)
 
-__device__ __forceinline__ void adj_cp8(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+__device__ __forceinline__ void adj_cp16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void adj_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending> __device__ __forceinline__ void adj_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 __global__ void __launch_bounds__(32 * ADJS_WARPS)
 adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhaseArgs g) {
-    __shared__ double ring[ADJS_WARPS][ADJS_DEPTH][2][NS][NS];   // [slot][mid | low][row k][column]
+    __shared__ __align__(16) double ring[ADJS_WARPS][ADJS_DEPTH][2][NS][ADJ_MROW];   // [slot][mid | low][row k][column, padded]
     const AdjointArgs& a = g.a;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * ADJS_WARPS + warp;
@@ -189,7 +202,7 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
     double* __restrict__ st_out = g.stages + (size_t)i * adj_stages_per_condition(S) * NS;
     const int total = (NTOT - 1) * S;
     // row k of M at node `node` -> registers (first node only) / shared-memory ring (everything else)
-    auto row_src = [&](size_t node) { return g.nodes + (node * ADJ_NF + ADJ_F_M + (size_t)k * NS) * n + i; };
+    auto row_src = [&](size_t node) { return g.nodes + adj_m_offset(node, k, (size_t)i, n); };
     auto issue = [&](int q) {   // sub-step q = (800 - kk) S + ss: its mid-point node and its lower node
         if (q < total && sp) {
             const int kk = NTOT - 1 - q / S, ss = q % S;
@@ -198,9 +211,9 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
             double* dm = &ring[warp][q % ADJS_DEPTH][0][k][0];
             double* dl = &ring[warp][q % ADJS_DEPTH][1][k][0];
 #pragma unroll
-            for (int c = 0; c < NS; c++) {
-                adj_cp8(dm + c, m + (size_t)c * n);
-                adj_cp8(dl + c, l + (size_t)c * n);
+            for (int c = 0; c < ADJ_MROW; c += 2) {
+                adj_cp16(dm + c, m + c);
+                adj_cp16(dl + c, l + c);
             }
         }
         adj_cp_commit();   // (an empty group past the end keeps the group count in step with q)
@@ -222,7 +235,7 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
     {
         const double* r0 = row_src((size_t)(NTOT - 1));   // knot 800
 #pragma unroll
-        for (int c = 0; c < NS; c++) up[c] = sp ? r0[(size_t)c * n] : 0.0;
+        for (int c = 0; c < NS; c++) up[c] = sp ? r0[c] : 0.0;
     }
     double tb = (double)a.tgrid[(size_t)(NTOT - 1) * n + i];
     double yb = a.y_knots[((size_t)(NTOT - 1) * NS + k) * n + i];
@@ -285,9 +298,9 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
 // a contraction over 6400 stages with 189 outputs per condition.  One block per condition; the stages go through shared memory
 // in chunks: all threads load a chunk (independent loads, nothing sequential), 9 x chunk threads form mu, then thread e < 189
 // accumulates its own entry over the chunk in stage order (fixed order: bit-reproducible).
-constexpr int ADJG_THREADS = 256, ADJG_CHUNK = 64;
+constexpr int ADJG_THREADS = 192, ADJG_CHUNK = 64;
 
-__global__ void __launch_bounds__(ADJG_THREADS, 4)   // 64 registers: four blocks per SM, all 640 conditions of a training batch resident at once
+__global__ void __launch_bounds__(ADJG_THREADS, 5)   // five blocks per SM = 740 resident: all 640 conditions of a training batch in one wave
 adjoint_grad_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhaseArgs g) {
     __shared__ double Vs[ADJG_CHUNK][21], Us[ADJG_CHUNK][18], Gm[ADJG_CHUNK][NS], Ws[ADJG_CHUNK], wout_s[NS][NR];
     __shared__ size_t node_s[ADJG_CHUNK];
@@ -299,7 +312,7 @@ adjoint_grad_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhase
     if (tid < 99) { ia = tid / 9; ib = tid % 9; }                                     // w_in[k][j]: wv_k mu_j
     else if (tid < 108) { ia = 11; ib = tid - 99; }                                   // w_b[j]:     1 * mu_j
     else if (tid < NPAR) { ia = 12 + (tid - 108) / 9; ib = 9 + (tid - 108) % 9; }     // w_out[i][j]: lt_i r_j
-    double G = 0.0;
+    double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0;   // four partial sums: the accumulation is a chain of dependent FMAs otherwise
     const double inv_sub = 1.0 / (double)S;
     const int total = (int)adj_stages_per_condition(S);
     const double* __restrict__ st_in = g.stages + (size_t)i * adj_stages_per_condition(S) * NS;
@@ -317,14 +330,14 @@ adjoint_grad_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhase
         __syncthreads();
         for (int t = tid; t < cn * NS; t += ADJG_THREADS) {
             const int s = t / NS, j = t % NS;
-            const double* rec = g.nodes + node_s[s] * ADJ_NF * n + i;
+            const double* rec = g.nodes + adj_v_offset(node_s[s], 0, (size_t)i, n);
             Vs[s][12 + j] = st_in[(size_t)(c0 + s) * NS + j] * rec[(size_t)(ADJ_F_MD + j) * n];   // lt_j = lam_j [du_j unclamped]
             Us[s][9 + j] = rec[(size_t)(ADJ_F_R + j) * n];
             Gm[s][j] = rec[(size_t)(ADJ_F_G + j) * n];
         }
         for (int t = tid; t < cn * (NS + 2); t += ADJG_THREADS) {
             const int s = t / (NS + 2), r = t % (NS + 2);
-            Vs[s][r] = g.nodes[(node_s[s] * ADJ_NF + ADJ_F_WV + r) * n + i];
+            Vs[s][r] = g.nodes[adj_v_offset(node_s[s], ADJ_F_WV + r, (size_t)i, n)];
         }
         __syncthreads();
         for (int t = tid; t < cn * NR; t += ADJG_THREADS) {   // mu_j = g_j sum_i lt_i wout[i][j]
@@ -339,11 +352,19 @@ adjoint_grad_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhase
             Us[s][j] = ((s0 + s1) + s2) * Gm[s][j];
         }
         __syncthreads();
-        if (tid < NPAR)
-            for (int s = 0; s < cn; s++) G = fma(Ws[s] * Vs[s][ia], Us[s][ib], G);
+        if (tid < NPAR) {
+            int s = 0;
+            for (; s + 3 < cn; s += 4) {
+                G0 = fma(Ws[s] * Vs[s][ia], Us[s][ib], G0);
+                G1 = fma(Ws[s + 1] * Vs[s + 1][ia], Us[s + 1][ib], G1);
+                G2 = fma(Ws[s + 2] * Vs[s + 2][ia], Us[s + 2][ib], G2);
+                G3 = fma(Ws[s + 3] * Vs[s + 3][ia], Us[s + 3][ib], G3);
+            }
+            for (; s < cn; s++) G0 = fma(Ws[s] * Vs[s][ia], Us[s][ib], G0);
+        }
         __syncthreads();
     }
-    if (tid < NPAR) a.grad[(size_t)tid * n + i] = G;
+    if (tid < NPAR) a.grad[(size_t)tid * n + i] = (G0 + G1) + (G2 + G3);
 }
 
 }  // namespace pfr

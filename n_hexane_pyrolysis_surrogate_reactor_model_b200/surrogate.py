@@ -196,9 +196,28 @@ class Surrogate:
         except Exception:
             pass
 
+    def _same_length(self, what: str, **cols):
+        """Every per-condition column of a call must have as many entries as T: the kernels index all of them with the same i."""
+        n = None
+        for name, t in cols.items():
+            if t is None:
+                continue
+            if t.dim() != 1:
+                raise _lib.PfrError(f"{what}: {name} must be one-dimensional, got shape {tuple(t.shape)}")
+            n = t.numel() if n is None else n
+            if t.numel() != n:
+                raise _lib.PfrError(f"{what}: {name} has {t.numel()} entries, expected {n}")
+        return n
+
+    def _need(self, what, name, t, dtype, shape):
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            got = type(t).__name__ if not isinstance(t, torch.Tensor) else f"{t.dtype} {tuple(t.shape)} on {t.device}, contiguous={t.is_contiguous()}"
+            raise _lib.PfrError(f"{what}: {name} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}, got {got}")
+
     # ------------------------------------------------------------------ a1
     def inlet_concentration(self, T, P) -> torch.Tensor:
         T, P = _f32(T, self.device), _f32(P, self.device)
+        self._same_length("inlet_concentration", T=T, P=P)
         c0 = torch.empty_like(T)
         _lib.check(_lib.lib().pfr_inlet_concentration(_ptr(T), _ptr(P), T.numel(), _ptr(c0), _stream()), "pfr_inlet_concentration")
         return c0
@@ -224,7 +243,11 @@ class Surrogate:
         T, P = _f32(T, self.device), _f32(P, self.device)
         L = None if L is None else _f32(L, self.device)
         u0 = None if u0 is None else _f32(u0, self.device)
-        n = T.numel()
+        n = self._same_length("time_grid", T=T, P=P, L=L, u0=u0)
+        if out is not None:
+            self._need("time_grid", "out", out, torch.float32, (NTOTAL, n))
+        if end_out is not None:
+            self._need("time_grid", "end_out", end_out, torch.float32, (n,))
         ws = self._workspace(n, ws_slot)
         grid = (out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)) if want_grid else None
         tend = (end_out if end_out is not None else torch.empty(n, dtype=torch.float32, device=self.device)) if want_end else None
@@ -236,7 +259,9 @@ class Surrogate:
         if self.temp_mlp is None:
             raise _lib.PfrError("this model set has no temperature MLP (Eoff variant)")
         T, P = _f32(T, self.device), _f32(P, self.device)
-        n = T.numel()
+        n = self._same_length("temp_profile", T=T, P=P)
+        if out is not None:
+            self._need("temp_profile", "out", out, torch.float32, (NTOTAL, n))
         ws = self._workspace(n, ws_slot)
         prof = out if out is not None else torch.empty((NTOTAL, n), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib().pfr_temp_profile(self.temp_mlp.handle, _ptr(T), _ptr(P), n, _ptr(prof), int(raw), _ptr(ws),
@@ -245,6 +270,8 @@ class Surrogate:
 
     def idx_cut(self, t_full: torch.Tensor, t_end: torch.Tensor) -> torch.Tensor:
         n = t_end.numel()
+        self._need("idx_cut", "t_end", t_end, torch.float32, (n,))
+        self._need("idx_cut", "t_full", t_full, torch.float32, (NTOTAL, n))
         idx = torch.empty(n, dtype=torch.int32, device=self.device)
         _lib.check(_lib.lib().pfr_idx_cut(_ptr(t_full), _ptr(t_end), n, _ptr(idx), _stream()), "pfr_idx_cut")
         return idx
@@ -293,11 +320,8 @@ class Surrogate:
         """The kernels take raw pointers: anything that is not exactly the layout they index would be read as garbage or out of
         bounds, so it is refused here."""
         def need(name, t, dtype, shape):
-            if t is None:
-                return
-            if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype or tuple(t.shape) != shape or not t.is_contiguous():
-                got = f"{type(t).__name__}" if not isinstance(t, torch.Tensor) else f"{t.dtype} {tuple(t.shape)} on {t.device}, contiguous={t.is_contiguous()}"
-                raise _lib.PfrError(f"integrate: {name} must be a contiguous {dtype} tensor of shape {shape} on {self.device}, got {got}")
+            if t is not None:
+                self._need("integrate", name, t, dtype, shape)
         need("c0", c0, torch.float32, (n,))
         need("tgrid", tgrid, torch.float32, (NTOTAL, n))
         need("Tprof", Tprof, torch.float32, (NTOTAL, n))
@@ -312,10 +336,7 @@ class Surrogate:
         T, P = _f32(T, self.device), _f32(P, self.device)
         L = None if L is None else _f32(L, self.device)
         u0 = None if u0 is None else _f32(u0, self.device)
-        n = T.numel()
-        for name, t in (("P", P), ("L", L), ("u0", u0)):
-            if t is not None and t.numel() != n:
-                raise _lib.PfrError(f"sweep: {name} has {t.numel()} entries, T has {n}")
+        n = self._same_length("sweep", T=T, P=P, L=L, u0=u0)
         dt = torch.float64 if precision == 64 else torch.float32
         y = torch.empty((NS, n), dtype=dt, device=self.device)
         status = torch.empty(n, dtype=torch.int32, device=self.device)

@@ -716,3 +716,31 @@ def test_status_reports_max_steps(surrogates, golden):
     tend = torch.as_tensor(golden["Eoff/tgrid"][:, -1].copy()).cuda()
     res = s.integrate(golden["T"], golden["c0"][:, 6], t_end=tend, rtol=1e-10, atol=1e-10, max_steps=3)
     assert set(res.status.cpu().numpy().tolist()) == {1}
+
+
+def test_raw_pointer_arguments_are_validated(surrogates, golden):
+    """The kernels index raw pointers: wrong dtype / shape / contiguity / length is refused on the host instead of being read as
+    garbage or out of bounds."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    s = surrogates("LLNL", "Eon")
+    tg = torch.as_tensor(golden["Eon/tgrid_full"].T.copy()).cuda()
+    Tp = torch.as_tensor(golden["Eon/Tprof"].T.copy()).cuda()
+    idx = torch.as_tensor(golden["Eon/idx_cut"].copy()).cuda()
+    T0, c0 = golden["T"], golden["c0"][:, 6]
+    ok = s.integrate(T0, c0, tgrid=tg, Tprof=Tp, idx_end=idx)
+    assert int(ok.status.abs().sum()) == 0
+    bad_calls = [dict(tgrid=tg.double(), Tprof=Tp, idx_end=idx),                       # float64 grid
+                 dict(tgrid=tg[:, ::2], Tprof=Tp[:, ::2], idx_end=idx[::2].contiguous()),   # non-contiguous columns
+                 dict(tgrid=tg, Tprof=Tp, idx_end=idx.long()),                          # int64 outlet knots
+                 dict(tgrid=tg[:800].contiguous(), Tprof=Tp, idx_end=idx),              # 800 instead of 801 knots
+                 dict(tgrid=tg, Tprof=Tp, idx_end=idx, perm=torch.arange(15, dtype=torch.int32, device="cuda"))]   # short permutation
+    for kw in bad_calls:
+        n = kw["idx_end"].numel()
+        with pytest.raises(_lib.PfrError):
+            s.integrate(T0[:n], c0[:n], **kw)
+    with pytest.raises(_lib.PfrError):
+        s.time_grid(golden["T"], golden["P"][:5])                                       # P shorter than T
+    with pytest.raises(_lib.PfrError):
+        s.sweep(golden["T"], golden["P"], golden["L"][:3], golden["U"], method="bs23")
+    with pytest.raises(_lib.PfrError):
+        s.idx_cut(tg.double(), tg[800].contiguous())
