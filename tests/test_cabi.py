@@ -51,6 +51,35 @@ def test_argument_validation_without_a_device():
     assert L.pfr_temp_profile(None, None, None, 0, None, 0, None, 0, 0, None) == 0
 
 
+def test_round2_entry_points_validate_without_a_device():
+    """pfr_sweep_*, pfr_stiff_fallback, crnn_model_update, pfr_loss_grad_staged: argument errors are reported before CUDA is
+    touched; the size helpers are pure host arithmetic."""
+    import ctypes
+    import numpy as np
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.pfr_sweep_create(None, None, None, 16, ctypes.byref(h)) == -1
+    assert L.pfr_sweep_run(None, None, None, None, None, 4, 4, 64, 1e-6, 1e-6, 0, 0, None, None, None, None, None, None, None) == -1
+    assert L.pfr_sweep_run(None, None, None, None, None, 0, 4, 64, 1e-6, 1e-6, 0, 0, None, None, None, None, None, None, None) == 0   # empty batch
+    assert L.pfr_sweep_destroy(None) == 0
+    assert L.pfr_stiff_fallback(None, 3, 64, 4, None, None, None, None, None, None, 1e-6, 1e-6, 0, 0, None, None, None, None, None, None) == -1
+    assert L.pfr_reduce_rows_ok(None, 3, 4, None, None, None) == -1
+    # one model handle, updated in place (host memory only: works without a GPU)
+    w_in, w_b, w_out = np.ones((11, 9), np.float32), np.ones(9, np.float32), np.ones((9, 9), np.float32)
+    fp = lambda a: a.ctypes.data_as(_lib.c_float_p)
+    assert L.crnn_model_create(fp(w_in), fp(w_b), fp(w_out), None, ctypes.byref(h)) == 0
+    assert L.crnn_model_update(h, fp(2 * w_in), fp(w_b), fp(w_out)) == 0
+    assert L.crnn_model_update(h, None, fp(w_b), fp(w_out)) == -1
+    assert L.crnn_model_destroy(h) == 0
+    # workspace arithmetic: 3201 nodes x 128 doubles + 6400 stages x 9 doubles per condition at two sub-steps
+    assert L.pfr_loss_grad_workspace_bytes(640, 2) == (3201 * 128 + 6400 * 9) * 640 * 8
+    assert L.pfr_loss_grad_workspace_bytes(0, 2) == 0
+    assert L.pfr_loss_grad_staged(None, 4, None, None, None, None, None, None, 2, None, None, None, 0, None) == -1
+    eon = L.pfr_sweep_device_bytes(1 << 20, 1)
+    assert 11.0e9 < eon < 12.5e9 and L.pfr_sweep_device_bytes(1 << 20, 0) < eon / 5    # two [801][n] grids (6.7 GB) + three MLP workspaces (1.7 GB each)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     import pytest
     from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib

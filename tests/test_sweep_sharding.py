@@ -48,7 +48,10 @@ def _worker(rank, world, port, n_total, ret):
     lo, hi = shard_bounds(n_total, world, rank)
     full = torch.arange(9 * n_total, dtype=torch.float64).reshape(9, n_total)
     got = gather_outlets(full[:, lo:hi].contiguous(), n_total)
-    ret[rank] = bool(torch.equal(got, full))
+    blocks = gather_outlets(full[:, lo:hi].contiguous(), n_total, as_blocks=True).blocks()    # views of the persistent buffer, no copy
+    views_ok = all(torch.equal(b, full[:, slice(*shard_bounds(n_total, world, r))]) for r, b in enumerate(blocks))
+    again = gather_outlets(2 * full[:, lo:hi].contiguous(), n_total)                          # the buffer is reused by the next sweep
+    ret[rank] = bool(torch.equal(got, full)) and views_ok and bool(torch.equal(again, 2 * full))
     dist.destroy_process_group()
 
 
