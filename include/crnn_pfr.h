@@ -186,7 +186,7 @@ int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float* tgrid, co
 /* The same loss and gradient (RK4 adjoint, `substeps` > 0 per knot interval) in three kernels: node quantities and the 9 x 9
  * Jacobian transposes of all conditions x intervals at once, the sequential adjoint walk (one mat-vec per stage, one warp per
  * condition), the parameter-gradient quadrature in parallel.  4-5x faster than pfr_loss_grad for a training batch of a few
- * hundred conditions; needs pfr_loss_grad_workspace_bytes(n, substeps) of device memory (3.7 MB per condition at 2 sub-steps). */
+ * hundred conditions; needs pfr_loss_grad_workspace_bytes(n, substeps) of device memory (3.8 MB per condition at 2 sub-steps). */
 size_t pfr_loss_grad_workspace_bytes(int n, int substeps);
 int pfr_loss_grad_staged(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof, const double* y_knots,
                          const float* ref, const float* yscale, int substeps, double* loss, double* grad, void* workspace,

@@ -23,11 +23,13 @@
 
 namespace pfr {
 
-// Node record, 128 doubles per condition:
+// Node record, 130 doubles per condition, both parts contiguous per condition so that every consumer moves 16-byte pieces:
 //   M part   [row k = 0..8][condition][10]   row k of M = J^T padded to 10 doubles: a lane of the adjoint walk fetches its row as five
 //                                            16-byte copies, and a warp of the node kernel stores 32 adjacent rows contiguously
-//   vectors  [field = 0..37][condition]      wv[11] | g[9] = r [z unclamped] | r[9] | md[9]
-constexpr int ADJ_MROW = 10, ADJ_NV = 38, ADJ_NF = NS * ADJ_MROW + ADJ_NV;
+//   vectors  [condition][40]                 wv[11] | g[9] = r [z unclamped] | r[9] | md[9] | 2 pad   (measured against
+//                                            [field][condition]: node kernel 0.59 -> 0.80 ms, gradient kernel 1.72 -> 1.08 ms)
+// Stage record [condition][stage][9]: lam at the RK4 stage; the four stages of a sub-step are 288 contiguous bytes.
+constexpr int ADJ_MROW = 10, ADJ_NV = 40, ADJ_NF = NS * ADJ_MROW + ADJ_NV, ADJ_SREC = NS;
 constexpr int ADJ_F_WV = 0, ADJ_F_G = 11, ADJ_F_R = 20, ADJ_F_MD = 29;
 constexpr int ADJP_BLOCK = 128;
 
@@ -39,11 +41,11 @@ __host__ __device__ inline size_t adj_stages_per_condition(int S) { return (size
 struct AdjPhaseArgs {
     AdjointArgs a;
     double* nodes;    // [nodes_per_condition] records of ADJ_NF * n doubles: M part, then vectors (layout above)
-    double* stages;   // [n][stages_per_condition][9]: lam at every RK4 stage, stage index ((kk - 1) S + ss) 4 + st
+    double* stages;   // [n][stages_per_condition][ADJ_SREC]: lam at every RK4 stage + its weight, stage index ((kk - 1) S + ss) 4 + st
 };
 
 __host__ __device__ inline size_t adj_m_offset(size_t node, int k, size_t i, size_t n) { return (node * ADJ_NF + (size_t)k * ADJ_MROW) * n + i * ADJ_MROW; }
-__host__ __device__ inline size_t adj_v_offset(size_t node, int field, size_t i, size_t n) { return (node * ADJ_NF + (size_t)NS * ADJ_MROW + field) * n + i; }
+__host__ __device__ inline size_t adj_v_offset(size_t node, size_t i, size_t n) { return (node * ADJ_NF + (size_t)NS * ADJ_MROW) * n + i * ADJ_NV; }
 
 // ---------------------------------------------------------------------------------------------------------------- phase 1
 // forward quantities + M = J^T at (T, y); the record is stored unless rec == nullptr; returns f
@@ -76,14 +78,16 @@ __device__ __forceinline__ void adj_node_full(const CrnnParams<double>& p, const
     }
     if (node < 0) return;
     // (the vectors that only phase 3 needs leave first, so that their registers are free while M is assembled)
-    double* __restrict__ rv = nodes + adj_v_offset((size_t)node, 0, i, n);
+    {
+        double v[ADJ_NV];
 #pragma unroll
-    for (int e = 0; e < NS + 2; e++) rv[(size_t)(ADJ_F_WV + e) * n] = wv[e];
+        for (int e = 0; e < NS + 2; e++) v[ADJ_F_WV + e] = wv[e];
 #pragma unroll
-    for (int j = 0; j < NR; j++) {
-        rv[(size_t)(ADJ_F_G + j) * n] = g[j];
-        rv[(size_t)(ADJ_F_R + j) * n] = r[j];
-        rv[(size_t)(ADJ_F_MD + j) * n] = md[j];
+        for (int j = 0; j < NR; j++) { v[ADJ_F_G + j] = g[j]; v[ADJ_F_R + j] = r[j]; v[ADJ_F_MD + j] = md[j]; }
+        v[ADJ_NV - 2] = v[ADJ_NV - 1] = 0.0;
+        double2* __restrict__ rv = reinterpret_cast<double2*>(nodes + adj_v_offset((size_t)node, i, n));   // 320-byte records
+#pragma unroll
+        for (int e = 0; e < ADJ_NV / 2; e++) rv[e] = make_double2(v[2 * e], v[2 * e + 1]);
     }
     // M[k][i] = q_k md_i sum_j nu[k][j] g_j wout[i][j]   ((J^T lam)_k = sum_i M[k][i] lam_i)
 #pragma unroll
@@ -186,9 +190,22 @@ __device__ __forceinline__ void adj_cp16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void adj_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending> __device__ __forceinline__ void adj_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
+__device__ __forceinline__ void adj_cp8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void adj_cp4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
 __global__ void __launch_bounds__(32 * ADJS_WARPS)
 adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhaseArgs g) {
     __shared__ __align__(16) double ring[ADJS_WARPS][ADJS_DEPTH][2][NS][ADJ_MROW];   // [slot][mid | low][row k][column, padded]
+    // Per-interval scalars of the LOWER knot of an interval (its time, this lane's state component, this lane's label) travel through
+    // a second ring by cp.async as well.  (As plain loads "one interval ahead" they did not prefetch anything: the compiler moved the
+    // loaded register into the variable's register right behind the load, and 37 % of this kernel's stall samples sat on those two
+    // moves -- ncu source page, profiles/r02e_ncu_full_training_kernels.txt.)
+    struct KnotSlot { double y; float t, ref; };
+    __shared__ __align__(16) KnotSlot knots[ADJS_WARPS][ADJS_DEPTH + 1][32];
     const AdjointArgs& a = g.a;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * ADJS_WARPS + warp;
@@ -199,21 +216,28 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
     const int k = sp ? lane : 0;
     const double wnorm = 1.0 / (double)(NOBS * NTOT), inv_sub = 1.0 / (double)S;
     const double isc = (lane < NOBS) ? 1.0 / (double)a.yscale[(size_t)lane * n + i] : 1.0;
-    double* __restrict__ st_out = g.stages + (size_t)i * adj_stages_per_condition(S) * NS;
+    double* __restrict__ st_out = g.stages + (size_t)i * adj_stages_per_condition(S) * ADJ_SREC;
     const int total = (NTOT - 1) * S;
-    // row k of M at node `node` -> registers (first node only) / shared-memory ring (everything else)
     auto row_src = [&](size_t node) { return g.nodes + adj_m_offset(node, k, (size_t)i, n); };
-    auto issue = [&](int q) {   // sub-step q = (800 - kk) S + ss: its mid-point node and its lower node
-        if (q < total && sp) {
-            const int kk = NTOT - 1 - q / S, ss = q % S;
-            const double* m = row_src(adj_interior_node(kk, 2 * ss, S));
-            const double* l = row_src(ss == S - 1 ? (size_t)(kk - 1) : adj_interior_node(kk, 2 * ss + 1, S));
-            double* dm = &ring[warp][q % ADJS_DEPTH][0][k][0];
-            double* dl = &ring[warp][q % ADJS_DEPTH][1][k][0];
+    auto issue = [&](int q) {   // sub-step q = (800 - kk) S + ss: its mid-point node and its lower node; with ss = 0 the lower knot's scalars
+        if (q < total) {
+            const int kk = NTOT - 1 - q / S, ss = q - (q / S) * S;
+            if (sp) {
+                const double* m = row_src(adj_interior_node(kk, 2 * ss, S));
+                const double* l = row_src(ss == S - 1 ? (size_t)(kk - 1) : adj_interior_node(kk, 2 * ss + 1, S));
+                double* dm = &ring[warp][q % ADJS_DEPTH][0][k][0];
+                double* dl = &ring[warp][q % ADJS_DEPTH][1][k][0];
 #pragma unroll
-            for (int c = 0; c < ADJ_MROW; c += 2) {
-                adj_cp16(dm + c, m + c);
-                adj_cp16(dl + c, l + c);
+                for (int c = 0; c < ADJ_MROW; c += 2) {
+                    adj_cp16(dm + c, m + c);
+                    adj_cp16(dl + c, l + c);
+                }
+            }
+            if (ss == 0) {
+                KnotSlot* ks = &knots[warp][(q / S) % (ADJS_DEPTH + 1)][lane];
+                adj_cp4(&ks->t, a.tgrid + (size_t)(kk - 1) * n + i);
+                if (sp) adj_cp8(&ks->y, a.y_knots + ((size_t)(kk - 1) * NS + k) * n + i);
+                if (lane < NOBS) adj_cp4(&ks->ref, a.ref + ((size_t)(kk - 1) * NOBS + lane) * n + i);
             }
         }
         adj_cp_commit();   // (an empty group past the end keeps the group count in step with q)
@@ -238,41 +262,36 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
         for (int c = 0; c < NS; c++) up[c] = sp ? r0[c] : 0.0;
     }
     double tb = (double)a.tgrid[(size_t)(NTOT - 1) * n + i];
-    double yb = a.y_knots[((size_t)(NTOT - 1) * NS + k) * n + i];
-    float ref_n = lane < NOBS ? a.ref[((size_t)(NTOT - 1) * NOBS + lane) * n + i] : 0.f;
-    float ta_n = a.tgrid[(size_t)(NTOT - 2) * n + i];
-    double ya_n = a.y_knots[((size_t)(NTOT - 2) * NS + k) * n + i];
+    double yb = sp ? a.y_knots[((size_t)(NTOT - 1) * NS + k) * n + i] : 0.0;
+    float ref_b = lane < NOBS ? a.ref[((size_t)(NTOT - 1) * NOBS + lane) * n + i] : 0.f;   // label of the knot whose state is yb
     double hs = 0.0, ta = 0.0, ya = 0.0;
-    auto knot_jump = [&](int kk) {             // loss term and adjoint jump at knot kk (its state is yb)
-        const float ref_c = ref_n;
-        if (kk > 0 && lane < NOBS) ref_n = a.ref[((size_t)(kk - 1) * NOBS + lane) * n + i];
+    float ref_a = 0.f;
+    auto knot_jump = [&]() {             // loss term and adjoint jump at the knot whose state / label are yb / ref_b
         if (lane < NOBS) {
             const double pc = m_min(m_max(yb, p.lb), p.ub);
-            const double d = (pc - (double)ref_c) * isc;
+            const double d = (pc - (double)ref_b) * isc;
             loss = fma(d, d, loss);
             if (yb >= p.lb && yb <= p.ub) lam += 2.0 * d * isc * wnorm;
         }
     };
     for (int q = 0; q < total; q++) {
-        const int kk = NTOT - 1 - q / S, ss = q % S;
+        const int iv = q / S, kk = NTOT - 1 - iv, ss = q - iv * S;
+        adj_cp_wait<ADJS_DEPTH - 1>();   // this lane's copies for sub-step q have landed
         if (ss == 0) {
-            knot_jump(kk);
-            ta = (double)ta_n;
-            ya = ya_n;
-            if (kk > 1) {
-                ta_n = a.tgrid[(size_t)(kk - 2) * n + i];
-                ya_n = a.y_knots[((size_t)(kk - 2) * NS + k) * n + i];
-            }
+            knot_jump();
+            const KnotSlot& ks = knots[warp][iv % (ADJS_DEPTH + 1)][lane];
+            ta = (double)ks.t;
+            ya = sp ? ks.y : 0.0;
+            ref_a = lane < NOBS ? ks.ref : 0.f;
             hs = (tb - ta) * inv_sub;
         }
-        adj_cp_wait<ADJS_DEPTH - 1>();   // this lane's copies for sub-step q have landed
 #pragma unroll
         for (int c = 0; c < NS; c++) {
             mid[c] = sp ? ring[warp][q % ADJS_DEPTH][0][k][c] : 0.0;
             low[c] = sp ? ring[warp][q % ADJS_DEPTH][1][k][c] : 0.0;
         }
-        issue(q + ADJS_DEPTH);             // refills the slot that was just read (same lane, program order)
-        double* so = st_out + ((size_t)((kk - 1) * S + ss) * 4) * NS;
+        issue(q + ADJS_DEPTH);             // refills the slots that were just read (same lane, program order)
+        double* so = st_out + ((size_t)((kk - 1) * S + ss) * 4) * ADJ_SREC;
         const double l1 = lam;
         const double k1 = matvec(up, l1);
         const double l2 = fma(0.5 * hs, k1, lam);
@@ -281,13 +300,13 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
         const double k3 = matvec(mid, l3);
         const double l4 = fma(hs, k3, lam);
         const double k4 = matvec(low, l4);
-        if (sp) { so[lane] = l1; so[NS + lane] = l2; so[2 * NS + lane] = l3; so[3 * NS + lane] = l4; }
+        if (sp) { so[lane] = l1; so[ADJ_SREC + lane] = l2; so[2 * ADJ_SREC + lane] = l3; so[3 * ADJ_SREC + lane] = l4; }
         lam += hs / 6.0 * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
 #pragma unroll
         for (int c = 0; c < NS; c++) up[c] = low[c];
-        if (ss == S - 1) { tb = ta; yb = ya; }
+        if (ss == S - 1) { tb = ta; yb = ya; ref_b = ref_a; }
     }
-    knot_jump(0);
+    knot_jump();   // knot 0
     double lsum = lane < NOBS ? loss : 0.0;
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     if (lane == 0) a.loss[i] = lsum * wnorm;
@@ -296,73 +315,92 @@ adjoint_sweep_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhas
 // ---------------------------------------------------------------------------------------------------------------- phase 3
 // G[e] = sum over the RK4 stages s of  w_s V_s[ia(e)] U_s[ib(e)],  V = [wv(11), 1, lt(9)], U = [mu(9), r(9)]  (adjoint.cuh, header):
 // a contraction over 6400 stages with 189 outputs per condition.  One block per condition; the stages go through shared memory
-// in chunks: all threads load a chunk (independent loads, nothing sequential), 9 x chunk threads form mu, then thread e < 189
-// accumulates its own entry over the chunk in stage order (fixed order: bit-reproducible).
-constexpr int ADJG_THREADS = 192, ADJG_CHUNK = 64;
+// in chunks, double-buffered: while chunk c is contracted, the stage and node-vector records of chunk c + 1 are in flight
+// (cp.async, 16 bytes per copy: both record types are contiguous per condition).  Per chunk: 9 x chunk threads form lt and mu, then
+// thread e < 189 accumulates its own entry in stage order in four interleaved partial sums (fixed order: bit-reproducible).
+constexpr int ADJG_THREADS = 192, ADJG_CHUNK = 32;
 
+template <int kS>   // sub-steps per interval as a compile-time constant (0: read a.substeps): the stage -> node arithmetic divides by it
 __global__ void __launch_bounds__(ADJG_THREADS, 5)   // five blocks per SM = 740 resident: all 640 conditions of a training batch in one wave
 adjoint_grad_kernel(const __grid_constant__ CrnnParams<double> p, const AdjPhaseArgs g) {
-    __shared__ double Vs[ADJG_CHUNK][21], Us[ADJG_CHUNK][18], Gm[ADJG_CHUNK][NS], Ws[ADJG_CHUNK], wout_s[NS][NR];
-    __shared__ size_t node_s[ADJG_CHUNK];
+    __shared__ __align__(16) double Srec[2][ADJG_CHUNK][ADJ_SREC];   // lam(9) of every stage of the chunk: one contiguous range of the stage records
+    __shared__ __align__(16) double Vrec[2][ADJG_CHUNK][ADJ_NV];     // wv(11), g(9), r(9), md(9), pad
+    __shared__ float Tk[2][ADJG_CHUNK][2];                           // knot times of the stage's interval (quadrature weight)
+    __shared__ double Lt[ADJG_CHUNK][NS], Mu[ADJG_CHUNK][NR], Wt[ADJG_CHUNK], wout_s[NS][NR];
     const AdjointArgs& a = g.a;
-    const int tid = threadIdx.x, i = blockIdx.x, S = a.substeps;
+    const int tid = threadIdx.x, i = blockIdx.x, S = kS ? kS : a.substeps;
     const size_t n = (size_t)a.n;
     for (int e = tid; e < NS * NR; e += ADJG_THREADS) wout_s[e / NR][e % NR] = p.wout[e / NR][e % NR];
-    int ia = 11, ib = 0;
-    if (tid < 99) { ia = tid / 9; ib = tid % 9; }                                     // w_in[k][j]: wv_k mu_j
-    else if (tid < 108) { ia = 11; ib = tid - 99; }                                   // w_b[j]:     1 * mu_j
-    else if (tid < NPAR) { ia = 12 + (tid - 108) / 9; ib = 9 + (tid - 108) % 9; }     // w_out[i][j]: lt_i r_j
-    double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0;   // four partial sums: the accumulation is a chain of dependent FMAs otherwise
+    // entry e = tid:  w_in[k][j]: wv_k mu_j | w_b[j]: mu_j | w_out[i][j]: lt_i r_j   ->  (source of the first factor, index, source of the second, index)
+    int ka = 0, ia = 0, ib = 0;   // ka: 0 = wv (Vrec), 1 = one, 2 = lt
+    if (tid < 99) { ka = 0; ia = ADJ_F_WV + tid / 9; ib = tid % 9; }
+    else if (tid < 108) { ka = 1; ib = tid - 99; }
+    else if (tid < NPAR) { ka = 2; ia = (tid - 108) / 9; ib = (tid - 108) % 9; }
+    double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0;
     const double inv_sub = 1.0 / (double)S;
     const int total = (int)adj_stages_per_condition(S);
-    const double* __restrict__ st_in = g.stages + (size_t)i * adj_stages_per_condition(S) * NS;
-    for (int c0 = 0; c0 < total; c0 += ADJG_CHUNK) {
+    const double* __restrict__ st_in = g.stages + (size_t)i * adj_stages_per_condition(S) * ADJ_SREC;
+    auto issue = [&](int c0, int buf) {   // copies of the chunk that starts at stage c0 (nothing past the end)
         const int cn = min(ADJG_CHUNK, total - c0);
-        if (tid < cn) {   // node and quadrature weight of stage c0 + tid
-            const int stage = c0 + tid, q = stage >> 2, st = stage & 3, kk = q / S + 1, ss = q % S;
-            node_s[tid] = st == 0 ? (ss == 0 ? (size_t)kk : adj_interior_node(kk, 2 * ss - 1, S))
-                                  : (st == 3 ? (ss == S - 1 ? (size_t)(kk - 1) : adj_interior_node(kk, 2 * ss + 1, S))
-                                             : adj_interior_node(kk, 2 * ss, S));
-            const double hs = ((double)a.tgrid[(size_t)kk * n + i] - (double)a.tgrid[(size_t)(kk - 1) * n + i]) * inv_sub;
-            Ws[tid] = (st == 0 || st == 3) ? hs / 6.0 : hs / 3.0;
-            Vs[tid][11] = 1.0;
+        if (cn > 0) {
+            // chunks start at a multiple of 32 stages = 8 sub-steps = 2304 bytes, and a condition's stage records at a multiple of
+            // 4 x 9 x 8 bytes: the chunk is one 16-byte-aligned contiguous range
+            for (int t = tid; t < cn * ADJ_SREC / 2; t += ADJG_THREADS) adj_cp16(&Srec[buf][0][0] + 2 * t, st_in + (size_t)c0 * ADJ_SREC + 2 * t);
+            if (tid < 2 * cn) {
+                const int s = tid >> 1, q = (c0 + s) >> 2, kk = q / S + 1;
+                adj_cp4(&Tk[buf][s][tid & 1], a.tgrid + (size_t)(kk - (tid & 1)) * n + i);   // [0] = t(kk), [1] = t(kk - 1)
+            }
+            for (int t = tid; t < cn * (ADJ_NV / 2); t += ADJG_THREADS) {
+                const int s = t / (ADJ_NV / 2), c = t % (ADJ_NV / 2);
+                const int stage = c0 + s, q = stage >> 2, st = stage & 3, kk = q / S + 1, ss = q % S;
+                const size_t node = st == 0 ? (ss == 0 ? (size_t)kk : adj_interior_node(kk, 2 * ss - 1, S))
+                                            : (st == 3 ? (ss == S - 1 ? (size_t)(kk - 1) : adj_interior_node(kk, 2 * ss + 1, S))
+                                                       : adj_interior_node(kk, 2 * ss, S));
+                adj_cp16(&Vrec[buf][s][2 * c], g.nodes + adj_v_offset(node, (size_t)i, n) + 2 * c);
+            }
         }
-        __syncthreads();
+        adj_cp_commit();
+    };
+    issue(0, 0);
+    int buf = 0;
+    for (int c0 = 0; c0 < total; c0 += ADJG_CHUNK, buf ^= 1) {
+        const int cn = min(ADJG_CHUNK, total - c0);
+        issue(c0 + ADJG_CHUNK, buf ^ 1);
+        adj_cp_wait<1>();      // this thread's copies of chunk c0 have landed ...
+        __syncthreads();       // ... and so have everybody else's
         for (int t = tid; t < cn * NS; t += ADJG_THREADS) {
             const int s = t / NS, j = t % NS;
-            const double* rec = g.nodes + adj_v_offset(node_s[s], 0, (size_t)i, n);
-            Vs[s][12 + j] = st_in[(size_t)(c0 + s) * NS + j] * rec[(size_t)(ADJ_F_MD + j) * n];   // lt_j = lam_j [du_j unclamped]
-            Us[s][9 + j] = rec[(size_t)(ADJ_F_R + j) * n];
-            Gm[s][j] = rec[(size_t)(ADJ_F_G + j) * n];
+            Lt[s][j] = Srec[buf][s][j] * Vrec[buf][s][ADJ_F_MD + j];   // lt_j = lam_j [du_j unclamped]
         }
-        for (int t = tid; t < cn * (NS + 2); t += ADJG_THREADS) {
-            const int s = t / (NS + 2), r = t % (NS + 2);
-            Vs[s][r] = g.nodes[adj_v_offset(node_s[s], ADJ_F_WV + r, (size_t)i, n)];
+        if (tid < cn) {   // RK4 quadrature weight of the stage: hs / 6 for the first and last stage of a sub-step, hs / 3 for the middle ones
+            const double hs = ((double)Tk[buf][tid][0] - (double)Tk[buf][tid][1]) * inv_sub;
+            const int st = (c0 + tid) & 3;
+            Wt[tid] = (st == 0 || st == 3) ? hs / 6.0 : hs / 3.0;
         }
         __syncthreads();
-        for (int t = tid; t < cn * NR; t += ADJG_THREADS) {   // mu_j = g_j sum_i lt_i wout[i][j]
+        for (int t = tid; t < cn * NR; t += ADJG_THREADS) {            // mu_j = g_j sum_i lt_i wout[i][j]
             const int s = t / NR, j = t % NR;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                s0 = fma(Vs[s][12 + r], wout_s[r][j], s0);
-                s1 = fma(Vs[s][15 + r], wout_s[r + 3][j], s1);
-                s2 = fma(Vs[s][18 + r], wout_s[r + 6][j], s2);
+                s0 = fma(Lt[s][r], wout_s[r][j], s0);
+                s1 = fma(Lt[s][r + 3], wout_s[r + 3][j], s1);
+                s2 = fma(Lt[s][r + 6], wout_s[r + 6][j], s2);
             }
-            Us[s][j] = ((s0 + s1) + s2) * Gm[s][j];
+            Mu[s][j] = ((s0 + s1) + s2) * Vrec[buf][s][ADJ_F_G + j];
         }
         __syncthreads();
         if (tid < NPAR) {
+            auto term = [&](int s) {
+                const double va = ka == 0 ? Vrec[buf][s][ia] : (ka == 1 ? 1.0 : Lt[s][ia]);
+                const double ub = ka == 2 ? Vrec[buf][s][ADJ_F_R + ib] : Mu[s][ib];
+                return Wt[s] * va * ub;
+            };
             int s = 0;
-            for (; s + 3 < cn; s += 4) {
-                G0 = fma(Ws[s] * Vs[s][ia], Us[s][ib], G0);
-                G1 = fma(Ws[s + 1] * Vs[s + 1][ia], Us[s + 1][ib], G1);
-                G2 = fma(Ws[s + 2] * Vs[s + 2][ia], Us[s + 2][ib], G2);
-                G3 = fma(Ws[s + 3] * Vs[s + 3][ia], Us[s + 3][ib], G3);
-            }
-            for (; s < cn; s++) G0 = fma(Ws[s] * Vs[s][ia], Us[s][ib], G0);
+            for (; s + 3 < cn; s += 4) { G0 += term(s); G1 += term(s + 1); G2 += term(s + 2); G3 += term(s + 3); }
+            for (; s < cn; s++) G0 += term(s);
         }
-        __syncthreads();
+        __syncthreads();       // the buffers of this chunk are free for the copies issued in the next iteration
     }
     if (tid < NPAR) a.grad[(size_t)tid * n + i] = (G0 + G1) + (G2 + G3);
 }

@@ -1013,7 +1013,7 @@ extern "C" int pfr_loss_grad(crnn_model_t m, int n, const float* T0, const float
 // sequential adjoint walk reduced to one 9 x 9 mat-vec per stage, the parameter-gradient quadrature in parallel.
 extern "C" size_t pfr_loss_grad_workspace_bytes(int n, int substeps) {
     if (n < 1 || substeps < 1) return 0;
-    return ((size_t)adj_nodes_per_condition(substeps) * ADJ_NF + (size_t)adj_stages_per_condition(substeps) * NS) * (size_t)n * sizeof(double);
+    return ((size_t)adj_nodes_per_condition(substeps) * ADJ_NF + (size_t)adj_stages_per_condition(substeps) * ADJ_SREC) * (size_t)n * sizeof(double);
 }
 
 extern "C" int pfr_loss_grad_staged(crnn_model_t m, int n, const float* T0, const float* tgrid, const float* Tprof, const double* y_knots,
@@ -1038,7 +1038,12 @@ extern "C" int pfr_loss_grad_staged(crnn_model_t m, int n, const float* T0, cons
     CK_LAUNCH("adjoint_nodes_kernel");
     adjoint_sweep_kernel<<<(unsigned)((n + ADJS_WARPS - 1) / ADJS_WARPS), 32 * ADJS_WARPS, 0, st>>>(m->pd, g);
     CK_LAUNCH("adjoint_sweep_kernel");
-    adjoint_grad_kernel<<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g);
+    switch (substeps) {   // sub-steps per interval as a compile-time constant where it is one of the usual values
+        case 1: adjoint_grad_kernel<1><<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g); break;
+        case 2: adjoint_grad_kernel<2><<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g); break;
+        case 3: adjoint_grad_kernel<3><<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g); break;
+        default: adjoint_grad_kernel<0><<<(unsigned)n, ADJG_THREADS, 0, st>>>(m->pd, g);
+    }
     CK_LAUNCH("adjoint_grad_kernel");
     return PFR_OK;
 }

@@ -186,7 +186,7 @@ class CrnnTrainer:
         # latency-bound and nine lanes per right-hand side make it ~4x shorter than one thread per condition, "bs23")
         self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "bs23w")
         self._crnn, self._bufs, self.failed_last = None, {}, 0
-        # gradient kernels: "staged" = three kernels with a workspace of 3.7 MB per condition (pfr_loss_grad_staged), "warp" = the
+        # gradient kernels: "staged" = three kernels with a workspace of 3.8 MB per condition (pfr_loss_grad_staged), "warp" = the
         # single kernel, one condition per warp, no workspace (pfr_loss_grad); "auto" = staged while the workspace stays under 8 GB
         self.adjoint = os.environ.get("PFR_TRAIN_ADJOINT", "auto")
         self._adj_ws = None

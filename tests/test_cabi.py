@@ -72,8 +72,8 @@ def test_round2_entry_points_validate_without_a_device():
     assert L.crnn_model_update(h, fp(2 * w_in), fp(w_b), fp(w_out)) == 0
     assert L.crnn_model_update(h, None, fp(w_b), fp(w_out)) == -1
     assert L.crnn_model_destroy(h) == 0
-    # workspace arithmetic: 3201 nodes x 128 doubles + 6400 stages x 9 doubles per condition at two sub-steps
-    assert L.pfr_loss_grad_workspace_bytes(640, 2) == (3201 * 128 + 6400 * 9) * 640 * 8
+    # workspace arithmetic: 3201 nodes x 130 doubles + 6400 stages x 9 doubles per condition at two sub-steps
+    assert L.pfr_loss_grad_workspace_bytes(640, 2) == (3201 * 130 + 6400 * 9) * 640 * 8
     assert L.pfr_loss_grad_workspace_bytes(0, 2) == 0
     assert L.pfr_loss_grad_staged(None, 4, None, None, None, None, None, None, 2, None, None, None, 0, None) == -1
     eon = L.pfr_sweep_device_bytes(1 << 20, 1)
