@@ -87,9 +87,13 @@ int pfr_mlp_create(int in_dim, const float* const weights[4], const float* const
                    double out_max, const double* in_lo, const double* in_hi, pfr_mlp_t* out);
 int pfr_mlp_destroy(pfr_mlp_t mlp);
 /* Arithmetic of the three 512-wide layers: PFR_MLP_FP32 = FP32 FFMA, one accumulator per output, k ascending (default);
- * PFR_MLP_TF32X3 = tcgen05 tensor cores with an error-compensated 3xTF32 split (float32 accumulation in TMEM). */
+ * PFR_MLP_TF32X3 = tcgen05 tensor cores with an error-compensated 3xTF32 split (float32 accumulation in TMEM);
+ * PFR_MLP_F16X3 = the same three-product split with FLOAT16 operand pairs (same 11-bit significands, half the bytes and half
+ * the instructions; the low part is scaled by 2^11 so that it stays a normal float16).  Needs every fc2..fc4 weight inside
+ * float16's range, else pfr_mlp_set_mode returns PFR_EINVAL; activations beyond 65 504 become NaN in the grid. */
 #define PFR_MLP_FP32 0
 #define PFR_MLP_TF32X3 1
+#define PFR_MLP_F16X3 2
 int pfr_mlp_set_mode(pfr_mlp_t mlp, int mode);
 /* scratch needed by the calls below for batches processed `chunk` conditions at a time (chunk<=0: default) */
 size_t pfr_mlp_workspace_bytes(int n, int chunk);

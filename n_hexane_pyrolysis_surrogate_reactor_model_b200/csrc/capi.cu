@@ -1,6 +1,7 @@
 // C-ABI entry points (include/crnn_pfr.h): handle management, argument checks, kernel launches.
 #include "../../include/crnn_pfr.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -58,9 +59,12 @@ struct pfr_mlp {
     float *W1, *b1, *Wt2, *b2, *Wt3, *b3, *Wt4, *b4;
     float span, omin;
     MlpInputScale sc;
-    // tensor-core path (mlp_tc.cuh): TF32 hi/lo split of fc2..fc4 in nn.Linear layout [out][512] and their TMA maps
-    int mode;  // PFR_MLP_FP32 | PFR_MLP_TF32X3
+    // tensor-core path (mlp_tc.cuh): hi/lo split of fc2..fc4 in nn.Linear layout [out][512] and their TMA maps -- TF32 pairs
+    // (float32 containers) and float16 pairs (lo scaled by 2^11); the maps describe whichever pair the mode uses
+    int mode;  // PFR_MLP_FP32 | PFR_MLP_TF32X3 | PFR_MLP_F16X3
     float *Whi[3], *Wlo[3];
+    __half *Whh[3], *Wlh[3];
+    bool f16_ok;  // every fc2..fc4 weight is inside float16's range
     CUtensorMap mapWhi[3], mapWlo[3];
 };
 
@@ -69,7 +73,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_tiled_fn g_encode = nullptr;
-static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows, bool half) {
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -78,10 +82,10 @@ static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint3
         g_encode = (encode_tiled_fn)fn;
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)tc::KDIM, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)tc::KDIM * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)tc::KDIM * (half ? sizeof(__half) : sizeof(float))};
+    const cuuint32_t box[2] = {(cuuint32_t)(half ? tc::Operand<true>::BK : tc::Operand<false>::BK), box_rows};   // one 128-byte row
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+    const CUresult r = g_encode(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -156,7 +160,8 @@ static int device_ctx(DeviceCtx** out) {
             CK(cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming));
         }
         // kernels that need more than 48 KB of dynamic shared memory
-        if ((rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true>, tc::SMEM_DYN)) ||
+        if ((rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false, false>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true, false>, tc::SMEM_DYN)) ||
+            (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false, true>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true, true>, tc::SMEM_DYN)) ||
             (rc = opt_in_smem(dp54_kernel<double>, dp54_smem_bytes<double>())) || (rc = opt_in_smem(dp54_kernel<float>, dp54_smem_bytes<float>())) ||
             (rc = opt_in_smem(rodas4_kernel<double, true, true>, (size_t)sm_entries<true>() * RODAS_BLOCK * sizeof(double))) ||
             (rc = opt_in_smem(rodas4_kernel<double, false, true>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(double))) ||
@@ -279,6 +284,7 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
         if (rc) { delete m; return rc; }
     }
     m->in_dim = in_dim;
+    m->f16_ok = true;
     m->npad4 = round_up(MLP_OUT, GEMM_BM);
     // `out * (max - min) + min`: (max - min) in double, both scalars rounded to float32 by the tensor op
     m->span = (float)(out_max - out_min);
@@ -321,6 +327,18 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
         }
         if ((rc = upload(hi, &m->Whi[l]))) return rc;
         if ((rc = upload(lo, &m->Wlo[l]))) return rc;
+        // float16 pairs: hi = rn_f16(w), lo' = rn_f16((w - hi) * 2^11)  (the difference and the scaling are exact in float32)
+        std::vector<__half> hh(hi.size()), lh(hi.size());
+        for (size_t e = 0; e < hh.size(); e++) {
+            const float w = weights[l + 1][e];
+            if (!(fabsf(w) <= 65504.f)) m->f16_ok = false;
+            hh[e] = __float2half_rn(w);
+            lh[e] = __float2half_rn((w - __half2float(hh[e])) * 2048.f);
+        }
+        CK(cudaMalloc((void**)&m->Whh[l], hh.size() * sizeof(__half)));
+        CK(cudaMemcpy(m->Whh[l], hh.data(), hh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&m->Wlh[l], lh.size() * sizeof(__half)));
+        CK(cudaMemcpy(m->Wlh[l], lh.data(), lh.size() * sizeof(__half), cudaMemcpyHostToDevice));
     }
     m->mode = PFR_MLP_FP32;
     *out = m;
@@ -328,18 +346,23 @@ extern "C" int pfr_mlp_create(int in_dim, const float* const weights[4], const f
 }
 
 extern "C" int pfr_mlp_set_mode(pfr_mlp_t m, int mode) {
-    if (!m || (mode != PFR_MLP_FP32 && mode != PFR_MLP_TF32X3)) return PFR_EINVAL;
+    if (!m || (mode != PFR_MLP_FP32 && mode != PFR_MLP_TF32X3 && mode != PFR_MLP_F16X3)) return PFR_EINVAL;
     {
         const int rc = check_device(m->device);
         if (rc) return rc;
     }
-    if (mode == PFR_MLP_TF32X3) {
+    if (mode == PFR_MLP_F16X3 && !m->f16_ok) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "PFR_MLP_F16X3: a weight of fc2..fc4 is outside float16's range; use PFR_MLP_TF32X3");
+        return PFR_EINVAL;
+    }
+    if (mode != PFR_MLP_FP32) {
+        const bool half = mode == PFR_MLP_F16X3;
         for (int l = 0; l < 3; l++) {
             const int rows = l < 2 ? MLP_HID : MLP_OUT;
             const uint32_t box = tc::BN;   // the 800-row output layer's last tile reads past the end: TMA zero-fills
             int rc;
-            if ((rc = make_map_2d(&m->mapWhi[l], m->Whi[l], rows, box))) return rc;
-            if ((rc = make_map_2d(&m->mapWlo[l], m->Wlo[l], rows, box))) return rc;
+            if ((rc = make_map_2d(&m->mapWhi[l], half ? (const void*)m->Whh[l] : (const void*)m->Whi[l], rows, box, half))) return rc;
+            if ((rc = make_map_2d(&m->mapWlo[l], half ? (const void*)m->Wlh[l] : (const void*)m->Wlo[l], rows, box, half))) return rc;
         }
     }
     m->mode = mode;
@@ -352,6 +375,10 @@ extern "C" int pfr_mlp_destroy(pfr_mlp_t m) {
                        m->Wlo[0], m->Wlo[1], m->Wlo[2]};
     for (float* p : ptrs)
         if (p) cudaFree(p);
+    for (int l = 0; l < 3; l++) {
+        if (m->Whh[l]) cudaFree(m->Whh[l]);
+        if (m->Wlh[l]) cudaFree(m->Wlh[l]);
+    }
     delete m;
     return PFR_OK;
 }
@@ -383,9 +410,9 @@ extern "C" int pfr_dev_set_tc_trace(unsigned long long* l2, unsigned long long* 
     return PFR_OK;
 }
 template <bool kFinal>
-static int launch_tc_gemm(const DeviceCtx& ctx, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
+static int launch_tc_gemm(const DeviceCtx& ctx, bool half, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
                           const tc::GemmArgs& g, cudaStream_t st) {
-    auto kern = tc::mlp_tc_gemm_kernel<kFinal>;
+    auto kern = half ? tc::mlp_tc_gemm_kernel<kFinal, true> : tc::mlp_tc_gemm_kernel<kFinal, false>;
     const int total = g.n_tiles * g.m_tiles;
     kern<<<total < ctx.num_sms ? total : ctx.num_sms, tc::THREADS, tc::SMEM_DYN, st>>>(ahi, alo, bhi, blo, g);   // persistent: one CTA per SM
     CK_LAUNCH("mlp_tc_gemm_kernel");
@@ -422,8 +449,10 @@ static int mlp_run_tc(pfr_mlp_t m, const float* T, const float* P, const float* 
         Bhi[l] = Hl + (size_t)2 * MLP_HID * ld;
         Blo[l] = Hl + (size_t)3 * MLP_HID * ld;
         Sl[l] = S + (size_t)l * MLP_OUT * ld;
-        if ((rc = make_map_2d(&mA[l][0][0], Ahi[l], ld, tc::BM)) || (rc = make_map_2d(&mA[l][0][1], Alo[l], ld, tc::BM)) ||
-            (rc = make_map_2d(&mA[l][1][0], Bhi[l], ld, tc::BM)) || (rc = make_map_2d(&mA[l][1][1], Blo[l], ld, tc::BM)))
+        // (float16 pairs use the first half of each array: the workspace layout does not depend on the mode)
+        const bool half = m->mode == PFR_MLP_F16X3;
+        if ((rc = make_map_2d(&mA[l][0][0], Ahi[l], ld, tc::BM, half)) || (rc = make_map_2d(&mA[l][0][1], Alo[l], ld, tc::BM, half)) ||
+            (rc = make_map_2d(&mA[l][1][0], Bhi[l], ld, tc::BM, half)) || (rc = make_map_2d(&mA[l][1][1], Blo[l], ld, tc::BM, half)))
             return rc;
     }
     cudaStream_t lane_stream[2] = {st, st};
@@ -455,20 +484,22 @@ static int mlp_run_tc_chunks(DeviceCtx& ctx, pfr_mlp_t m, const float* T, const 
         cudaStream_t ls = lane_stream[l];
         const int mv = (n - c0) < ld ? (n - c0) : ld;
         const int rows = round_up(mv, tc::BM);
-        tc::mlp_tc_layer1_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ls>>>(   // 8 warps per block, 8 rows per warp
+        const bool half = m->mode == PFR_MLP_F16X3;
+        auto layer1 = half ? tc::mlp_tc_layer1_kernel<true> : tc::mlp_tc_layer1_kernel<false>;
+        layer1<<<(unsigned)((rows + 63) / 64), 256, 0, ls>>>(   // 8 warps per block, 8 rows per warp
             m->W1, m->b1, m->in_dim, m->sc.lo[0], m->sc.lo[1], m->sc.lo[2], m->sc.lo[3], m->sc.span[0], m->sc.span[1],
             m->sc.span[2], m->sc.span[3], m->sc.fullL, m->sc.fullU, T + c0, P + c0, L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv,
             rows, Ahi[l], Alo[l]);
         CK_LAUNCH("mlp_tc_layer1_kernel");
         const int mt = rows / tc::BM;
         tc::GemmArgs g2{m->b2, Bhi[l], Blo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[0]};
-        if ((rc = launch_tc_gemm<false>(ctx, mA[l][0][0], mA[l][0][1], m->mapWhi[0], m->mapWlo[0], g2, ls))) return rc;
+        if ((rc = launch_tc_gemm<false>(ctx, half, mA[l][0][0], mA[l][0][1], m->mapWhi[0], m->mapWlo[0], g2, ls))) return rc;
         tc::GemmArgs g3{m->b3, Ahi[l], Alo[l], 0, 0, 0, 1.f, 0.f, MLP_HID / tc::BN, mt, g_tc_trace[1]};
-        if ((rc = launch_tc_gemm<false>(ctx, mA[l][1][0], mA[l][1][1], m->mapWhi[1], m->mapWlo[1], g3, ls))) return rc;
+        if ((rc = launch_tc_gemm<false>(ctx, half, mA[l][1][0], mA[l][1][1], m->mapWhi[1], m->mapWlo[1], g3, ls))) return rc;
         float* out_rows = grid ? grid + (size_t)n + c0 : Sl[l];
         const size_t out_ld = grid ? (size_t)n : (size_t)ld;
         tc::GemmArgs g4{m->b4, out_rows, nullptr, out_ld, MLP_OUT, mv, span, omin, (MLP_OUT + tc::BN - 1) / tc::BN, mt, g_tc_trace[2]};
-        if ((rc = launch_tc_gemm<true>(ctx, mA[l][0][0], mA[l][0][1], m->mapWhi[2], m->mapWlo[2], g4, ls))) return rc;
+        if ((rc = launch_tc_gemm<true>(ctx, half, mA[l][0][0], mA[l][0][1], m->mapWhi[2], m->mapWlo[2], g4, ls))) return rc;
         if (is_time) {
             if (!raw) {
                 enforce_strict_kernel<<<(mv + 255) / 256, 256, 0, ls>>>(out_rows, out_ld, mv, grid ? grid + c0 : nullptr,
@@ -499,7 +530,7 @@ static int mlp_run(pfr_mlp_t m, const float* T, const float* P, const float* L, 
     float* H1 = static_cast<float*>(ws);
     float* H2 = H1 + (size_t)MLP_HID * ld;
     float* S = H1 + (size_t)4 * MLP_HID * ld;  // [800][ld] scratch for the t_end-only mode
-    if (m->mode == PFR_MLP_TF32X3) return mlp_run_tc(m, T, P, L, U, n, grid, t_end, is_time, raw, H1, S, ld, st);
+    if (m->mode != PFR_MLP_FP32) return mlp_run_tc(m, T, P, L, U, n, grid, t_end, is_time, raw, H1, S, ld, st);
     const float span = raw ? 1.f : m->span, omin = raw ? 0.f : m->omin;
     for (int c0 = 0; c0 < n; c0 += ld) {
         const int mv = (n - c0) < ld ? (n - c0) : ld;

@@ -1,5 +1,6 @@
 // Tensor-core path of the predictor MLPs: tcgen05 (5th-gen tensor cores, TMEM accumulator) with an
-// error-compensated 3xTF32 split, operands staged by TMA into 128-byte-swizzled shared memory.
+// error-compensated three-product operand split, operands staged by TMA into 128-byte-swizzled shared memory.
+// Two operand formats, chosen per MLP handle (pfr_mlp_set_mode): TF32 pairs (round 1) and FLOAT16 pairs (round 2, default).
 //
 // Why a split: the grids the MLPs produce go through enforce_strict, whose keep/repair decisions hang on the
 // last bits of a float32 result, so a plain TF32 product (10-bit mantissa) is not acceptable.
@@ -14,6 +15,17 @@
 // the (2^-11 times smaller) cross terms -- and the epilogue adds the four in float32 round-to-nearest: ~21 truncating
 // adds per chain, the same error level as a 512-term FP32 FFMA chain.
 //
+// FLOAT16 pairs (kHalf): an 11-bit significand is an 11-bit significand -- float16 carries exactly as many bits as TF32, in half
+// the bytes, and kind::f16 issues K = 16 per instruction where kind::tf32 issues K = 8.  The split is
+//   hi = rn_f16(x),  lo' = rn_f16((x - hi) * 2^11)      (x - hi is exact in float32, the scaling keeps lo' a NORMAL float16
+// down to |x| ~ 1e-7; below that its absolute error is < 2^-35), a*b ~= hi_a*hi_b + 2^-11 (hi_a*lo'_b + lo'_a*hi_b):
+// the cross terms have their own accumulator anyway, so the 2^-11 is one exact multiply in the epilogue.  Same three
+// products, same accumulators, HALF the shared-memory bytes per product and half the instructions: the GEMM is bound by the
+// shared-memory bandwidth of SS-operand MMA and, in the sustained pass, by board power, and both scale
+// with the bytes.  The K-thirds are 11 instructions long instead of 21, so the truncating accumulation drifts less.  Range:
+// float16 tops out at 65 504 -- the shipped predictors' activations stay below 2 and their weights below 0.35; a weight
+// beyond the range makes pfr_mlp_set_mode refuse this mode, an activation beyond it turns into inf -> NaN in the grid (loud).
+//
 // Layout: activations are K-major here ([condition][512], hi and lo arrays), weights keep nn.Linear's [out][512]
 // (K-major as well), so both operands use the canonical K-major SWIZZLE_128B tile (8 rows x 128 B atoms, SBO 1024 B)
 // that TMA writes and the UMMA shared-memory descriptor reads.  D[128 conditions x BN outputs] lives in TMEM; the four
@@ -26,6 +38,7 @@
 // traps instead of hanging the device.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,13 +46,22 @@ namespace pfr {
 namespace tc {
 
 constexpr int BM = 128;      // conditions per CTA tile = UMMA M
-constexpr int BK = 32;       // floats per k-block: 128 bytes, one swizzle row
-constexpr int UMMA_K = 8;    // tf32: 32 bytes per instruction
 constexpr int STAGES = 3;
 constexpr int THREADS = 192;
 constexpr int KDIM = 512;
 constexpr int TMEM_COLS = 512;
 constexpr int BN = 128;     // outputs per CTA tile = UMMA N; four accumulators of BN columns fill the 512 TMEM columns
+
+// operand format: what one 128-byte swizzle row / one 32-byte instruction slice holds, and where the K-thirds are cut
+template <bool kHalf>
+struct Operand {
+    static constexpr int ESIZE = kHalf ? 2 : 4;
+    static constexpr int BK = 128 / ESIZE;          // elements per k-block: 128 bytes, one swizzle row
+    static constexpr int UMMA_K = 32 / ESIZE;       // elements per instruction: 32 bytes
+    static constexpr int NKB = KDIM / BK;           // k-blocks (= pipeline stages filled) per tile
+    static constexpr int KG = NKB * (BK / UMMA_K);  // instruction groups per tile: 64 | 32
+    static constexpr int CUT1 = KG / 3 + 1, CUT2 = 2 * KG / 3 + 1;   // 22, 43 | 11, 22
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,16 +102,27 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// cute::UMMA::InstrDescriptor: c F32 (1<<4), a/b TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// cute::UMMA::InstrDescriptor: c F32 (1<<4), a/b format at bits 7 / 10 (kind::tf32: TF32 = 2; kind::f16: F16 = 0), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24
+template <bool kHalf>
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+    return (1u << 4) | ((kHalf ? 0u : 2u) << 7) | ((kHalf ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
+template <bool kHalf>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kHalf) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -110,6 +143,27 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     uint64_t r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// the float16 pair of two float32 values: hi = rn_f16(r), lo' = rn_f16((r - hi) * 2^11), two values per packed word
+__device__ __forceinline__ void split_f16x2(float r0, float r1, uint32_t& hi2, uint32_t& lo2) {
+    const __half2 h = __floats2half2_rn(r0, r1);
+    const float2 hf = __half22float2(h);
+    uint32_t d0, d1;
+    unpack2(mul_f32x2(sub_f32x2(pack2(__float_as_uint(r0), __float_as_uint(r1)), pack2(__float_as_uint(hf.x), __float_as_uint(hf.y))),
+                      pack2(0x45000000u, 0x45000000u)), d0, d1);   // 2048.0f
+    const __half2 l = __floats2half2_rn(__uint_as_float(d0), __uint_as_float(d1));
+    hi2 = *reinterpret_cast<const uint32_t*>(&h);
+    lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // Round to TF32 (10 explicit mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 returns for every finite
@@ -132,7 +186,7 @@ struct GemmArgs {
     unsigned long long* trace;  // development (-DPFR_TC_TRACE, tools/trace_tc.py): [tiles][8] %globaltimer stamps, else nullptr
 };
 
-constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // rows of 128 bytes in both formats
 constexpr int EPI_COLS = 16;                               // accumulator columns per epilogue slab
 constexpr uint32_t SLAB_BYTES = 32 * EPI_COLS * 4;         // one warp's [32 conditions][16 outputs] slab of one array
 constexpr uint32_t STAGING_BYTES = 4 * 2 * SLAB_BYTES;     // four epilogue warps x (hi, lo)
@@ -169,7 +223,7 @@ __device__ __forceinline__ void tmem_load_slab(uint32_t (&v)[4][16], uint32_t tm
 // read the last accumulator slab.  Hidden layers leave through a warp-private shared-memory transpose so that one store
 // instruction writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces; the output layer stores
 // straight into the knot-major grid, where a warp's 32 conditions are contiguous.
-template <bool kFinal>
+template <bool kFinal, bool kHalf>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, const GemmArgs g) {
@@ -197,7 +251,8 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
-    constexpr int NKB = KDIM / BK;
+    using Op = Operand<kHalf>;
+    constexpr int NKB = Op::NKB, BK = Op::BK;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -218,7 +273,7 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            constexpr uint32_t idesc = umma_idesc<kHalf>(BN);
             uint32_t it = 0, lt = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, lt++) {
                 unsigned long long* tr = g.trace ? g.trace + 8 * (size_t)tile : nullptr;
@@ -236,15 +291,15 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                        const uint32_t off = ks * UMMA_K * 4;
-                        const int kg = kb * (BK / UMMA_K) + ks;          // 0..63
-                        const int part = kg < 22 ? 0 : (kg < 43 ? 1 : 2);  // three thirds of K for the leading term
-                        const bool first = kg == 0 || kg == 22 || kg == 43;
+                    for (int ks = 0; ks < 4; ks++) {                       // four 32-byte instruction slices per 128-byte row
+                        const uint32_t off = ks * 32;
+                        const int kg = kb * 4 + ks;                          // 0 .. Op::KG - 1
+                        const int part = kg < Op::CUT1 ? 0 : (kg < Op::CUT2 ? 1 : 2);  // three thirds of K for the leading term
+                        const bool first = kg == 0 || kg == Op::CUT1 || kg == Op::CUT2;
                         // cross terms -> accumulator 0 ; leading term -> accumulator 1 + part
-                        umma_tf32(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, kg != 0);
-                        umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1);
-                        umma_tf32(tmem_d + (uint32_t)((1 + part) * BN), umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, !first);
+                        umma_ss<kHalf>(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, kg != 0);
+                        umma_ss<kHalf>(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1);
+                        umma_ss<kHalf>(tmem_d + (uint32_t)((1 + part) * BN), umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, !first);
                     }
                     umma_commit(&empty_bar[s]);  // the stage is free once these MMAs have read it
                 }
@@ -294,13 +349,44 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     // instruction (add.rn.f32x2: the epilogue is bound by instruction issue)
                     const uint64_t main = add_f32x2(add_f32x2(pack2(w[1][j], w[1][j + 1]), pack2(w[2][j], w[2][j + 1])), pack2(w[3][j], w[3][j + 1]));
                     const float2 bb = *reinterpret_cast<const float2*>(&bias_s[c * EPI_COLS + j]);
-                    const uint64_t xx = add_f32x2(add_f32x2(main, pack2(w[0][j], w[0][j + 1])), pack2(__float_as_uint(bb.x), __float_as_uint(bb.y)));
+                    // (float16 pairs: the cross-term accumulator carries the 2^11 of lo'; 0x3a000000 = 2^-11, exact)
+                    const uint64_t with_cross = kHalf ? fma_f32x2(pack2(w[0][j], w[0][j + 1]), pack2(0x3a000000u, 0x3a000000u), main)
+                                                      : add_f32x2(main, pack2(w[0][j], w[0][j + 1]));
+                    const uint64_t xx = add_f32x2(with_cross, pack2(__float_as_uint(bb.x), __float_as_uint(bb.y)));
                     uint32_t x0, x1;
                     unpack2(xx, x0, x1);
                     x[j] = __uint_as_float(x0);
                     x[j + 1] = __uint_as_float(x1);
                 }
-                if (!kFinal) {
+                if constexpr (!kFinal && kHalf) {
+                    // float16 pairs: this slab is 32 bytes per row and array; two slabs make the 64-byte rows of the transpose
+                    uint32_t hp[8], lp[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) split_f16x2(fmaxf(x[j], 0.f), fmaxf(x[j + 1], 0.f), hp[j >> 1], lp[j >> 1]);
+                    if ((c & 1) == 0) __syncwarp();   // the previous pair of slabs has been read out
+                    const int fw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int chunk = 2 * (c & 1) + j;
+                        *reinterpret_cast<uint4*>(mine + lane * 64 + ((chunk ^ fw) << 4)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(mine + SLAB_BYTES + lane * 64 + ((chunk ^ fw) << 4)) =
+                            make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+                    }
+                    if (c & 1) {
+                        __syncwarp();
+                        __half* oh = reinterpret_cast<__half*>(g.out_hi);
+                        __half* ol = reinterpret_cast<__half*>(g.out_lo);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int row = (lane >> 2) + 8 * i, chunk = lane & 3, phys = chunk ^ ((row >> 1) & 3);
+                            const uint4 h4 = *reinterpret_cast<const uint4*>(mine + row * 64 + (phys << 4));
+                            const uint4 l4 = *reinterpret_cast<const uint4*>(mine + SLAB_BYTES + row * 64 + (phys << 4));
+                            const size_t off = (size_t)(m0 + 32 * q + row) * KDIM + (o0 - EPI_COLS) + 8 * chunk;
+                            *reinterpret_cast<uint4*>(oh + off) = h4;
+                            *reinterpret_cast<uint4*>(ol + off) = l4;
+                        }
+                    }
+                } else if constexpr (!kFinal) {
                     float hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
@@ -354,10 +440,11 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     }
 }
 
-// layer 1 (K <= 4) fused with the input scaling, written K-major as a TF32 hi/lo pair.
-// One warp per condition row: the four scaled inputs (IEEE divisions, as the reference computes them) once per lane,
-// then lane l produces outputs 4l..4l+3 (+128, +256, +384) so that every store instruction of the warp writes 512
-// contiguous bytes.  Memory-bound on the 4 KB it writes per condition.
+// layer 1 (K <= 4) fused with the input scaling, written K-major as a hi/lo pair (TF32 pairs in float32 containers, or
+// float16 pairs).  One warp per condition row: the four scaled inputs (IEEE divisions, as the reference computes them) once
+// per lane, then lane l produces 16 outputs in runs of 16 bytes per array so that every store instruction of the warp writes
+// 512 contiguous bytes.  Memory-bound on the 4 KB (2 KB) it writes per condition.
+template <bool kHalf>
 __global__ void __launch_bounds__(256)
 mlp_tc_layer1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, float lo0, float lo1, float lo2,
                      float lo3, float sp0, float sp1, float sp2, float sp3, float fullL, float fullU,
@@ -377,20 +464,33 @@ mlp_tc_layer1_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
         x[1] = __fdiv_rn(__fsub_rn(P[ms], lo1), sp1);
         x[2] = in_dim > 2 ? __fdiv_rn(__fsub_rn(L ? L[ms] : fullL, lo2), sp2) : 0.f;
         x[3] = in_dim > 2 ? __fdiv_rn(__fsub_rn(U ? U[ms] : fullU, lo3), sp3) : 0.f;
+        constexpr int RUN = kHalf ? 8 : 4;           // outputs per 16-byte store
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int k0 = 128 * j + 4 * lane;
-            float hi[4], lo[4];
+        for (int j = 0; j < KDIM / (32 * RUN); j++) {
+            const int k0 = 32 * RUN * j + RUN * lane;
+            float a[RUN];
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
+            for (int t = 0; t < RUN; t++) {
                 float acc = 0.f;
                 for (int i = 0; i < in_dim; i++) acc = fmaf(x[i], w_s[i * KDIM + k0 + t], acc);   // i ascending, like the FP32 path
-                acc = fmaxf(acc + b_s[k0 + t], 0.f);
-                hi[t] = rn_tf32(acc);
-                lo[t] = rn_tf32(acc - hi[t]);
+                a[t] = fmaxf(acc + b_s[k0 + t], 0.f);
             }
-            *reinterpret_cast<float4*>(Hhi + (size_t)m * KDIM + k0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(Hlo + (size_t)m * KDIM + k0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            if constexpr (kHalf) {
+                uint32_t hp[4], lp[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) split_f16x2(a[2 * t], a[2 * t + 1], hp[t], lp[t]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(Hhi) + (size_t)m * KDIM + k0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(Hlo) + (size_t)m * KDIM + k0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            } else {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    hi[t] = rn_tf32(a[t]);
+                    lo[t] = rn_tf32(a[t] - hi[t]);
+                }
+                *reinterpret_cast<float4*>(Hhi + (size_t)m * KDIM + k0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(Hlo + (size_t)m * KDIM + k0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
 }

@@ -80,6 +80,9 @@ class CrnnModel:
             pass
 
 
+MLP_MODES = {"fp32": 0, "tf32x3": 1, "f16x3": 2}
+
+
 class MlpModel:
     """Device-side handle of one 512-wide predictor MLP (pfr_mlp_create); weights are uploaded once."""
 
@@ -97,8 +100,9 @@ class MlpModel:
         self.set_mode(mode)
 
     def set_mode(self, mode: str):
-        """'fp32': FP32 FFMA layers (fixed summation order); 'tf32x3': tcgen05 tensor cores, 3xTF32 split."""
-        _lib.check(_lib.lib().pfr_mlp_set_mode(self.handle, {"fp32": 0, "tf32x3": 1}[mode]), "pfr_mlp_set_mode")
+        """'fp32': FP32 FFMA layers (fixed summation order); 'tf32x3': tcgen05 tensor cores, 3xTF32 split; 'f16x3': the same
+        split with float16 operand pairs (half the shared-memory bytes and instructions per product)."""
+        _lib.check(_lib.lib().pfr_mlp_set_mode(self.handle, MLP_MODES[mode]), "pfr_mlp_set_mode")
         self.mode = mode
 
     def __del__(self):

@@ -87,7 +87,7 @@ def test_rodas_three_lane_kernel_equals_thread_per_condition(surrogates, conditi
 
 
 # ----------------------------------------------------------------------------------------------- a2-a5
-@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("mech", ["LLNL", "JetSurf", "NUIG"])
 def test_time_mlp_raw_vs_torch_cpu(surrogates, model_sets, conditions, mech, mlp_mode):
     """Stage (i): network output before un-scaling vs torch CPU float32 (the reference's arithmetic), for both
@@ -108,7 +108,7 @@ def test_time_mlp_raw_vs_torch_cpu(surrogates, model_sets, conditions, mech, mlp
     assert np.max(np.abs(ref32 - ref64)) < 3e-6
 
 
-@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3", "f16x3"])
 def test_time_grid_matches_oracle(surrogates, model_sets, conditions, mlp_mode):
     """Un-scaled, enforce_strict-repaired grid.  A knot may flip between 'kept' and 'repaired' on a last-bit
     difference of the MLP output, which moves it by up to 1e-5 s; everything else agrees to float32 rounding."""
@@ -135,7 +135,7 @@ def test_time_grid_end_only_equals_full(surrogates, conditions):
     assert torch.equal(g[800], tend)                           # same kernels, bit-exact
 
 
-@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3", "f16x3"])
 def test_time_grid_chunking_and_ragged_sizes(model_sets, conditions, mlp_mode):
     """Batch sizes that are not multiples of the tile, and a chunk size that forces several passes."""
     from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import Surrogate
@@ -148,7 +148,7 @@ def test_time_grid_chunking_and_ragged_sizes(model_sets, conditions, mlp_mode):
         assert torch.equal(g, full[:, :n].contiguous())
 
 
-@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3", "f16x3"])
 def test_temp_profile_matches_oracle(surrogates, model_sets, conditions, mlp_mode):
     from oracle import reference_path as R
     T, P, _, _ = cond4(conditions)
@@ -471,7 +471,7 @@ def test_dopri5_eon_within_reference_noise(surrogates, golden):
 
 
 # ----------------------------------------------------------------------------------------------- end to end
-@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("mech,variant", [("LLNL", "Eoff"), ("LLNL", "Eon"), ("JetSurf", "Eoff"), ("JetSurf", "Eon"),
                                           ("NUIG", "Eoff"), ("NUIG", "Eon")])
 def test_sweep_end_to_end_vs_oracle(surrogates, model_sets, conditions, mech, variant, mlp_mode):
