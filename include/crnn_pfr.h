@@ -55,6 +55,11 @@ extern "C" {
 #define PFR_METHOD_BS23_WARP 6  /* PFR_METHOD_BS23 with ONE CONDITION PER WARP (lane = species = reaction; float64, tgrid required): the
                                  * latency-oriented mapping for batches of a few hundred conditions with dense output -- the forward
                                  * pass of the training step; same method and controller, dot products summed in another order */
+#define PFR_METHOD_TAYLOR4 7    /* explicit Taylor-series method of order 4 (3), one thread per condition, knot-limited (tgrid required): the time
+                                 * derivatives of f = W exp(kT + nu^T ln y) come from the series recurrences of log and exp, so a step costs ONE
+                                 * set of logarithms / exponentials and eight 9x9 mat-vecs instead of BS23's three right-hand sides; steps are cut
+                                 * where a species crosses the lower state clamp; PFR_ST_STIFF as for BS23.  stats[2] counts coefficient
+                                 * evaluations (one per attempt) */
 
 typedef struct crnn_model* crnn_model_t;
 typedef struct pfr_mlp* pfr_mlp_t;

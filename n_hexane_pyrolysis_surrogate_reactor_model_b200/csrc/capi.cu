@@ -19,6 +19,7 @@
 #include "integrate_rodas_coop.cuh"
 #include "integrate_explicit.cuh"
 #include "integrate_lanes.cuh"
+#include "integrate_taylor.cuh"
 #include "adjoint.cuh"
 #include "adjoint_phases.cuh"
 #include "mlp.cuh"
@@ -162,6 +163,7 @@ static int device_ctx(DeviceCtx** out) {
         // kernels that need more than 48 KB of dynamic shared memory
         if ((rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false, false>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true, false>, tc::SMEM_DYN)) ||
             (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<false, true>, tc::SMEM_DYN)) || (rc = opt_in_smem(tc::mlp_tc_gemm_kernel<true, true>, tc::SMEM_DYN)) ||
+            (rc = opt_in_smem(taylor4_kernel<double, true>, taylor_smem_bytes<double>())) || (rc = opt_in_smem(taylor4_kernel<double, false>, taylor_smem_bytes<double>())) ||
             (rc = opt_in_smem(dp54_kernel<double>, dp54_smem_bytes<double>())) || (rc = opt_in_smem(dp54_kernel<float>, dp54_smem_bytes<float>())) ||
             (rc = opt_in_smem(rodas4_kernel<double, true, true>, (size_t)sm_entries<true>() * RODAS_BLOCK * sizeof(double))) ||
             (rc = opt_in_smem(rodas4_kernel<double, false, true>, (size_t)sm_entries<false>() * RODAS_BLOCK * sizeof(double))) ||
@@ -683,9 +685,24 @@ static int dispatch_bs23(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasA
     if (rc) return rc;
     const int full = (a.n + BS23_BLOCK - 1) / BS23_BLOCK, persistent = BS23_CTAS_PER_SM * ctx.num_sms;
     const int grid = full < persistent ? full : persistent;
-    if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
-    else bs23_kernel<real, false><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, a);
+    CoefDup<real> cd;
+    fill_coef_dup(cd, p);
+    if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, cd, a);
+    else bs23_kernel<real, false><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, cd, a);
     CK_LAUNCH("bs23_kernel");
+    return PFR_OK;
+}
+
+template <typename real>
+static int dispatch_taylor4(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
+    RodasArgs a = a0;
+    int rc = next_counter(ctx, st, &a.work_counter);
+    if (rc) return rc;
+    const int full = (a.n + TAYLOR_BLOCK - 1) / TAYLOR_BLOCK, persistent = TAYLOR_CTAS_PER_SM * ctx.num_sms;
+    const int grid = full < persistent ? full : persistent;
+    if (a.Tprof) taylor4_kernel<real, true><<<grid, TAYLOR_BLOCK, taylor_smem_bytes<real>(), st>>>(p, a);
+    else taylor4_kernel<real, false><<<grid, TAYLOR_BLOCK, taylor_smem_bytes<real>(), st>>>(p, a);
+    CK_LAUNCH("taylor4_kernel");
     return PFR_OK;
 }
 
@@ -695,7 +712,9 @@ static int dispatch_dp54(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasA
     int rc = next_counter(ctx, st, &a.work_counter);
     if (rc) return rc;
     const int full = (a.n + DP54_BLOCK - 1) / DP54_BLOCK, persistent = DP54_CTAS_PER_SM * ctx.num_sms;
-    dp54_kernel<real><<<full < persistent ? full : persistent, DP54_BLOCK, dp54_smem_bytes<real>(), st>>>(p, a);
+    CoefDup<real> cd;
+    fill_coef_dup(cd, p);
+    dp54_kernel<real><<<full < persistent ? full : persistent, DP54_BLOCK, dp54_smem_bytes<real>(), st>>>(p, cd, a);
     CK_LAUNCH("dp54_kernel");
     return PFR_OK;
 }
@@ -717,6 +736,7 @@ static int integrate_launch(DeviceCtx& ctx, crnn_model_t m, int method, int prec
         case PFR_METHOD_ROS3: return d ? dispatch_rodas_coop<double, COOP_ROS3>(m->pd, a, st) : dispatch_rodas_coop<float, COOP_ROS3>(m->pf, a, st);
         case PFR_METHOD_DP54: return d ? dispatch_dp54<double>(ctx, m->pd, a, st) : dispatch_dp54<float>(ctx, m->pf, a, st);
         case PFR_METHOD_BS23: return d ? dispatch_bs23<double>(ctx, m->pd, a, st) : dispatch_bs23<float>(ctx, m->pf, a, st);
+        case PFR_METHOD_TAYLOR4: return d ? dispatch_taylor4<double>(ctx, m->pd, a, st) : dispatch_taylor4<float>(ctx, m->pf, a, st);
         case PFR_METHOD_BS23_WARP: {
             if (!d) return PFR_EINVAL;
             const int blocks = (a.n + LANES_WARPS - 1) / LANES_WARPS;
@@ -741,11 +761,11 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
     if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 &&
-        method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54 && method != PFR_METHOD_BS23_WARP)
+        method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54 && method != PFR_METHOD_BS23_WARP && method != PFR_METHOD_TAYLOR4)
         return PFR_EINVAL;
     if (method == PFR_METHOD_BS23_WARP && (!tgrid || precision != 64)) return PFR_EINVAL;   // knot-limited, float64 state
     if (method == PFR_METHOD_DP54 && (tgrid || !t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;   // isothermal outlet at t_end only
-    if (method == PFR_METHOD_BS23 && !tgrid) return PFR_EINVAL;   // the explicit fast path is the knot-limited stepper
+    if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_TAYLOR4) && !tgrid) return PFR_EINVAL;   // the explicit fast paths are knot-limited steppers
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     if (n == 0) return PFR_OK;
@@ -882,7 +902,7 @@ extern "C" int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, cons
     if (precision != 32 && precision != 64) return PFR_EINVAL;
     if (!(rtol > 0) || !(atol > 0)) return PFR_EINVAL;
     const bool eon = s->temp_mlp != nullptr;
-    if (eon ? (method != PFR_METHOD_BS23 && method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4)
+    if (eon ? (method != PFR_METHOD_BS23 && method != PFR_METHOD_TAYLOR4 && method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4)
             : (method != PFR_METHOD_DP54 && method != PFR_METHOD_ROS3 && method != PFR_METHOD_RODAS4))
         return PFR_EINVAL;
     if (!eon && !L) return PFR_EINVAL;   // the isothermal sweep integrates to the end of the (T, P, L, u0) grid
@@ -965,7 +985,7 @@ extern "C" int pfr_sweep_run(pfr_sweep_t s, const float* T, const float* P, cons
     CK(cudaEventRecord(s->k1[slot], st));
     s->runs++;
     // 6. conditions the explicit fast path flagged stiff go through the Rosenbrock kernel; the list is built and counted on the device
-    if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_DP54) && !(flags & PFR_SWEEP_NO_FALLBACK)) {
+    if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_TAYLOR4 || method == PFR_METHOD_DP54) && !(flags & PFR_SWEEP_NO_FALLBACK)) {
         int* count = stiff_count_out ? stiff_count_out : s->stiff_count;
         CK(cudaMemsetAsync(count, 0, sizeof(int), st));
         collect_status_kernel<<<blocks, 256, 0, st>>>(status, order, n, PFR_ST_STIFF, s->stiff_list, count);

@@ -70,6 +70,42 @@ struct TpcCoef {
     FastTables ft;
 };
 
+// Second feed of the same coefficients: the kernel-parameter constant bank, read through UNIFORM registers (LDCU.64, then
+// DFMA R, R, UR, R).  Measured on this part (tools/micro/coef_paths.cu, dfma_regs.cu): a 9x9 mat-vec whose coefficients all arrive
+// by broadcast LDS.128 runs at 45 % of the DFMA rate and one fed entirely by LDCU.64 at 50 %, at any occupancy, while the same
+// mat-vec with its coefficients in registers runs at 93 %: the feed costs as much as the arithmetic, whichever of the two paths
+// delivers it (a 16-byte shared-memory load returns 512 bytes per warp through the register file's write port, which the
+// 256-byte results of the DFMAs already keep busy; the constant cache serves one uniform load per clock and SM).  The two paths
+// are independent, so the rows of a mat-vec are SPLIT between them (PFR_UNIFORM_ROWS: bit k = row k comes through uniform
+// registers).  The block is stored twice and the copy toggles with every right-hand side -- a loop-carried, warp-uniform index --
+// because loads from a fixed parameter address are loop-invariant and both nvcc and ptxas would hoist all of them out of the
+// step loop (and spill them).
+#ifndef PFR_UNIFORM_ROWS
+#define PFR_UNIFORM_ROWS 0x1ff   // all nine rows of both mat-vecs (measured: 82.4 ms with none, 75.7 with three, 71.5 with six, 70.2 ms with all nine)
+#endif
+template <typename real>
+struct __align__(16) CoefDup {
+    real nu[2][NS][10];      // [copy][k][j]
+    real woutT[2][NR][10];   // [copy][j][i]
+    real arr[2][NR][4];      // [copy][j]: Ea_j, b_j, lnA_j, 0
+};
+template <typename real>
+static inline void fill_coef_dup(CoefDup<real>& d, const CrnnParams<real>& p) {
+    for (int c = 0; c < 2; c++)
+        for (int r = 0; r < NS; r++)
+            for (int e = 0; e < 10; e++) {
+                d.nu[c][r][e] = e < NR ? p.nu[r][e] : real(0);
+                d.woutT[c][r][e] = e < NS ? p.wout[e][r] : real(0);
+            }
+    for (int c = 0; c < 2; c++)
+        for (int j = 0; j < NR; j++) {
+            d.arr[c][j][0] = p.Ea[j];
+            d.arr[c][j][1] = p.b[j];
+            d.arr[c][j][2] = p.lnA[j];
+            d.arr[c][j][3] = real(0);
+        }
+}
+
 // volatile: the values are loop-invariant; a plain load lets the compiler hoist all of them out of the step loop.  `after`
 // is an artificial input: the load may not be scheduled before that value exists, which keeps the nine coefficient rows
 // of a mat-vec from being fetched (and held in 180 registers) ahead of the logarithms / exponentials they multiply.
@@ -106,11 +142,21 @@ __device__ __forceinline__ void arrhenius_tpc(const CrnnParams<real>& p, const T
     }
 }
 
+// the same with the coefficients from uniform registers (CoefDup)
+template <typename real>
+__device__ __forceinline__ void arrhenius_uni(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, real T, real (&kT)[NR]) {
+    const real invT = rcp_full(T);
+    const real mE = -p.inv_R * invT;
+    const real lnT = t_log<real>(T, sc.ft);
+#pragma unroll
+    for (int j = 0; j < NR; j++) kT[j] = fma(cd.arr[copy][j][0], mE, fma(cd.arr[copy][j][1], lnT, cd.arr[copy][j][2]));
+}
+
 // du = f(y) at given kT: streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
 // min(|zlo|, |zhi|) and min(|dulo|, |duhi|): the exponent and output clamps are skipped when no entry comes near them.
-template <typename real>
-__device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, const real (&kT)[NR],
-                                           const real (&y)[NS], real (&du)[NS]) {
+template <typename real, int kUniRows>
+__device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, int zthr, int dthr,
+                                           const real (&kT)[NR], const real (&y)[NS], real (&du)[NS]) {
     real z[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) z[j] = kT[j];
@@ -119,10 +165,15 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
         // (deciding the state clamp on the integer pipe -- high-word test, exact clamp only when some species is not strictly
         // inside -- was measured 6 % SLOWER than these 2 DSETP + 4 FSEL per species: the rare branch costs more than it saves)
         const real l = t_log<real>(m_min(m_max(y[k], p.lb), p.ub), sc.ft);
-        real c[10];
-        lds9(sc.nu[k], c, l);
+        if ((kUniRows >> k) & 1) {
 #pragma unroll
-        for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
+            for (int j = 0; j < NR; j++) z[j] = fma(cd.nu[copy][k][j], l, z[j]);
+        } else {
+            real c[10];
+            lds9(sc.nu[k], c, l);
+#pragma unroll
+            for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
+        }
     }
     bool near = false;
 #pragma unroll
@@ -136,10 +187,15 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
 #pragma unroll
     for (int j = 0; j < NR; j++) {
         const real r = t_exp<real>(z[j], sc.ft);
-        real c[10];
-        lds9(sc.woutT[j], c, r);
+        if ((kUniRows >> j) & 1) {
 #pragma unroll
-        for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
+            for (int i = 0; i < NS; i++) du[i] = fma(cd.woutT[copy][j][i], r, du[i]);
+        } else {
+            real c[10];
+            lds9(sc.woutT[j], c, r);
+#pragma unroll
+            for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
+        }
     }
     near = false;
 #pragma unroll
@@ -151,12 +207,14 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
 }
 
 // du = f(T, y)
-template <typename real>
-__device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, int zthr, int dthr, real T,
+template <typename real, int kUniRows>
+__device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, int zthr, int dthr, real T,
                                         const real (&y)[NS], real (&du)[NS]) {
     real kT[NR];
-    arrhenius_tpc<real>(p, sc, T, kT);
-    rhs_tpc_kT<real>(p, sc, zthr, dthr, kT, y, du);
+    arrhenius_tpc<real>(p, sc, T, kT);   // (its 27 coefficients stay on the shared-memory path: with them on the uniform path as well,
+                                         // ptxas 12.9 keeps the copy index in a vector register and every uniform load of the
+                                         // right-hand side turns into a per-thread constant load)
+    rhs_tpc_kT<real, kUniRows>(p, sc, cd, copy, zthr, dthr, kT, y, du);
 }
 
 // block-shared copy of the coefficients and tables (every kernel of this file starts with it)
@@ -182,11 +240,10 @@ __device__ __forceinline__ void load_tpc_coef(TpcCoef<real>& sc, const CrnnParam
 
 template <typename real, bool kRamp>
 __global__ void __launch_bounds__(BS23_BLOCK, PFR_BS23_MINB)
-bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+bs23_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ CoefDup<real> cd, const RodasArgs a) {
     __shared__ __align__(16) TpcCoef<real> sc;
     load_tpc_coef<real, BS23_BLOCK>(sc, p, a.tables);
     const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
-    const int lane = threadIdx.x & 31;
     const size_t n = (size_t)a.n;
     real* __restrict__ y_out = static_cast<real*>(a.y_out);
     real* __restrict__ y_dense = static_cast<real*>(a.y_dense);
@@ -202,6 +259,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     // produces the FSAL slope k1 and no second copy of the right-hand side is needed.
     bool have = false, fresh = false, exhausted = false;
     int i = 0, kend = 0, kc = 0, nacc = 0, nrej = 0, nrhs = 0, status = 0, stiff_cap = 0;
+    int ucopy = 0;   // which copy of the coefficient block the next right-hand side reads (CoefDup): warp-uniform, toggles
     double t = 0.0, t_final = 0.0, tk = 0.0, tk1 = 0.0, hprop = 0.0;
     real Tk = real(0), Tk1 = real(0), slope = real(0);
     float t_ahead = 0.f, T_ahead = 0.f;
@@ -224,14 +282,13 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     for (int k = 0; k < NS; k++) { y[k] = real(0); K1(k) = real(0); }
 
     while (true) {
-        const unsigned want = __ballot_sync(0xffffffffu, !have && !exhausted);
-        if (want) {
-            int base = 0;
-            const int leader = __ffs(want) - 1;
-            if (lane == leader) base = atomicAdd(a.work_counter, __popc(want));
-            base = __shfl_sync(0xffffffffu, base, leader);
+        {
+            // (a plain atomicAdd on a warp-uniform address: ptxas aggregates it itself -- one REDUX + one atomic per warp and
+            // round, consecutive slots to the requesting lanes in lane order.  Written out by hand with __ballot_sync /
+            // __shfl_sync, the compiler has to allow for a diverged warp at each of those, and with that every uniform-register
+            // load in the rest of the loop is lost.)
             if (!have && !exhausted) {
-                const int slot = base + __popc(want & ((1u << lane) - 1u));
+                const int slot = atomicAdd(a.work_counter, 1);
                 if (slot >= a.n) {
                     exhausted = true;
                 } else {
@@ -269,9 +326,13 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 }
             }
         }
-        if (__all_sync(0xffffffffu, !have)) break;
+        if (__reduce_or_sync(0xffffffffu, (unsigned)have) == 0u) break;   // (REDUX writes a uniform register: a uniform loop exit)
         bool done = have && !fresh && kc < 0;
-        if (have && !done) {
+        const bool active = have && !done;
+        // The stage loop is NOT under `if (active)`: uniform-register loads (the second coefficient feed, CoefDup) can only be issued
+        // from code in which the whole warp is known to be converged.  A lane without work evaluates the right-hand side on whatever
+        // its registers hold -- the warp executes those instructions anyway -- and takes no part in what follows the loop.
+        {
             const double dist = tk1 - t;
             const bool clip = !fresh && hprop * 1.01 >= dist;
             const double hs = fresh ? 0.0 : (clip ? dist : hprop);
@@ -284,11 +345,16 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             real k2[NS], w[NS];
 #pragma unroll
             for (int k = 0; k < NS; k++) w[k] = fma(real(0.5) * h, K1(k), y[k]);
+            const real T_last = clip ? Tk1 : fma(slope, h + tau, Tk);   // the stage at t + h: exactly the knot value on a clipped step
 #pragma unroll 1
             for (int stage = 0; stage < 3; stage++) {
-                const real cs = stage == 0 ? real(0.5) : (stage == 1 ? real(0.75) : real(1));
-                const real Ts = kRamp ? ((stage == 2 && clip) ? Tk1 : fma(slope, fma(cs, h, tau), Tk)) : Tk;
-                rhs_tpc<real>(p, sc, zthr, dthr, Ts, w, k2);
+                const real cs = stage == 0 ? real(0.5) : real(0.75);
+                const real Ts = kRamp ? (stage == 2 ? T_last : fma(slope, fma(cs, h, tau), Tk)) : Tk;
+                // `ucopy` is its own loop-carried variable on purpose: derived from `stage` it would share that variable's vector
+                // register (stage is compared against per-thread values), and an index in a vector register turns every
+                // uniform load into a per-thread constant load
+                rhs_tpc<real, PFR_UNIFORM_ROWS>(p, sc, cd, ucopy, zthr, dthr, Ts, w, k2);
+                ucopy ^= 1;
                 if (stage == 0) {
 #pragma unroll
                     for (int k = 0; k < NS; k++) {
@@ -305,6 +371,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                     }
                 }
             }   // k2 now holds k4 = f(t + h, y1): the next step's k1
+          if (active) {
             nrhs += 3;
             real e2 = real(0), d0 = real(0), d1 = real(0);
             bool finite = true;
@@ -377,6 +444,7 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             }
             if (!done && nacc + nrej > stiff_cap) { status = PFR_ST_STIFF_; done = true; }
             if (!done && nacc + nrej >= a.max_steps) { status = PFR_ST_MAXSTEPS_; done = true; }
+          }
         }
         if (done) {
             if (kc < 0) kc = 0;
@@ -444,19 +512,19 @@ __constant__ Dp54Tableau c_dp54 = {
 
 template <typename real>
 __global__ void __launch_bounds__(DP54_BLOCK, DP54_CTAS_PER_SM)
-dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
+dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ CoefDup<real> cd, const RodasArgs a) {
     __shared__ __align__(16) TpcCoef<real> sc;
     extern __shared__ __align__(16) unsigned char dp_dyn[];
     real* const ks = reinterpret_cast<real*>(dp_dyn) + threadIdx.x;   // slope k_s of species i: ks[(s * NS + i) * DP54_BLOCK]
     load_tpc_coef<real, DP54_BLOCK>(sc, p, a.tables);
     const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
-    const int lane = threadIdx.x & 31;
     const size_t n = (size_t)a.n;
     real* __restrict__ y_out = static_cast<real*>(a.y_out);
     const real rtol = real(a.rtol), atol = real(a.atol);
 
     bool have = false, fresh = false, exhausted = false;
     int i = 0, nacc = 0, nrej = 0, nrhs = 0, status = 0;
+    int ucopy = 0;   // copy of the coefficient block the next right-hand side reads (CoefDup): warp-uniform, toggles
     double t = 0.0, t_final = 0.0, hprop = 0.0;
     real y[NS], kT[NR];
 #pragma unroll
@@ -465,14 +533,13 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
     for (int j = 0; j < NR; j++) kT[j] = real(0);
 
     while (true) {
-        const unsigned want = __ballot_sync(0xffffffffu, !have && !exhausted);
-        if (want) {
-            int base = 0;
-            const int leader = __ffs(want) - 1;
-            if (lane == leader) base = atomicAdd(a.work_counter, __popc(want));
-            base = __shfl_sync(0xffffffffu, base, leader);
+        {
+            // (a plain atomicAdd on a warp-uniform address: ptxas aggregates it itself -- one REDUX + one atomic per warp and
+            // round, consecutive slots to the requesting lanes in lane order.  Written out by hand with __ballot_sync /
+            // __shfl_sync, the compiler has to allow for a diverged warp at each of those, and with that every uniform-register
+            // load in the rest of the loop is lost.)
             if (!have && !exhausted) {
-                const int slot = base + __popc(want & ((1u << lane) - 1u));
+                const int slot = atomicAdd(a.work_counter, 1);
                 if (slot >= a.n) {
                     exhausted = true;
                 } else {
@@ -490,17 +557,21 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                 }
             }
         }
-        if (__all_sync(0xffffffffu, !have)) break;
+        if (__reduce_or_sync(0xffffffffu, (unsigned)have) == 0u) break;   // (REDUX writes a uniform register: a uniform loop exit)
         bool done = have && !fresh && !(t_final > t);
-        if (have && !done) {
-            // a new condition enters with a zero-length step that runs stage 0 only: f(y0) for the first-step guess and FSAL
+        const bool active = have && !done;
+        // The stage loop has the same six rounds for every lane and is not under `if (active)`: uniform-register loads need a warp
+        // that is known to be converged (see bs23_kernel).  A new condition enters with a zero-length step -- every stage then
+        // evaluates f(y0), the last one leaves it where the first-step guess and the FSAL slot expect it (the warp runs six
+        // rounds for its other lanes anyway); a lane without work computes on whatever its registers hold.
+        {
             const double dist = t_final - t;
             const bool clip = !fresh && hprop * 1.01 >= dist;
             const double hs = fresh ? 0.0 : (clip ? dist : hprop);
             const real h = real(hs);
             real w[NS], f[NS];
 #pragma unroll 1
-            for (int s = fresh ? 0 : 1; s < (fresh ? 1 : DP54_STAGES); s++) {
+            for (int s = 1; s < DP54_STAGES; s++) {
 #pragma unroll
                 for (int k = 0; k < NS; k++) w[k] = real(0);
                 for (int j = 0; j < s; j++) {
@@ -509,11 +580,13 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
                     for (int k = 0; k < NS; k++) w[k] = fma(c, ks[(j * NS + k) * DP54_BLOCK], w[k]);
                 }
 #pragma unroll
-                for (int k = 0; k < NS; k++) w[k] = fma(h, w[k], y[k]);
-                rhs_tpc_kT<real>(p, sc, zthr, dthr, kT, w, f);
+                for (int k = 0; k < NS; k++) w[k] = fresh ? y[k] : fma(h, w[k], y[k]);   // (not h * stale slopes: they may be non-finite)
+                rhs_tpc_kT<real, PFR_UNIFORM_ROWS>(p, sc, cd, ucopy, zthr, dthr, kT, w, f);
+                ucopy ^= 1;
 #pragma unroll
                 for (int k = 0; k < NS; k++) ks[(s * NS + k) * DP54_BLOCK] = f[k];
             }
+          if (active) {
             nrhs += fresh ? 1 : DP54_STAGES - 1;
             // w = y1 (row 6 of the tableau = the 5th-order weights), f = f(y1)   [entry step: w = y0, f = f(y0), h = 0]
             real e2 = real(0), d0 = real(0), d1 = real(0);
@@ -563,6 +636,7 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const RodasArgs a) {
             }
             if (!done && nacc + nrej > DP54_MAX_ATTEMPTS) { status = PFR_ST_STIFF_; done = true; }
             if (!done && nacc + nrej >= a.max_steps) { status = PFR_ST_MAXSTEPS_; done = true; }
+          }
         }
         if (done) {
             const int io = a.out_index ? a.out_index[i] : i;   // column of the results (caller's order; pfr_sweep_run)

@@ -33,8 +33,8 @@
 // layers) or the float32 un-scaling (output layer, written straight into the [801][n] grid rows, coalesced over
 // conditions).
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one
-// elected lane), warps 2-5 epilogue.  Three 64 KB stages + 16 KB of epilogue slabs; every mbarrier wait is bounded and
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one
+// elected lane), warps 2-9 epilogue.  Three 64 KB stages + 32 KB of epilogue slabs; every mbarrier wait is bounded and
 // traps instead of hanging the device.
 #pragma once
 #include <cuda.h>
@@ -47,7 +47,11 @@ namespace tc {
 
 constexpr int BM = 128;      // conditions per CTA tile = UMMA M
 constexpr int STAGES = 3;
-constexpr int THREADS = 192;
+#ifndef PFR_TC_EPI_WARPS
+#define PFR_TC_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = PFR_TC_EPI_WARPS;   // 4: one warp per TMEM lane quarter; 8: two, each draining half of the columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int KDIM = 512;
 constexpr int TMEM_COLS = 512;
 constexpr int BN = 128;     // outputs per CTA tile = UMMA N; four accumulators of BN columns fill the 512 TMEM columns
@@ -189,7 +193,7 @@ struct GemmArgs {
 constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // rows of 128 bytes in both formats
 constexpr int EPI_COLS = 16;                               // accumulator columns per epilogue slab
 constexpr uint32_t SLAB_BYTES = 32 * EPI_COLS * 4;         // one warp's [32 conditions][16 outputs] slab of one array
-constexpr uint32_t STAGING_BYTES = 4 * 2 * SLAB_BYTES;     // four epilogue warps x (hi, lo)
+constexpr uint32_t STAGING_BYTES = EPI_WARPS * 2 * SLAB_BYTES;   // every epilogue warp x (hi, lo)
 constexpr size_t SMEM_DYN = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 
 #ifdef PFR_TC_TRACE
@@ -198,7 +202,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 #else
 #define TC_STAMP(ptr, slot) do { } while (0)
 #endif
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }   // the epilogue warps
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -232,7 +236,7 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     unsigned char* staging = smem + (size_t)STAGES * STAGE_BYTES;
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float bias_s[BN];
+    __shared__ __align__(16) float bias_s[BN];   // read as float2
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = g.n_tiles * g.m_tiles;
@@ -240,7 +244,7 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
-        mbar_init(&tmem_empty_bar, 4);   // one arrival per epilogue warp
+        mbar_init(&tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -308,17 +312,22 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             }
         }
     } else {
-        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread = one condition row
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ; thread = one condition row.  With eight warps, warps w and w + 4
+        // share a lane quarter and drain one half of the accumulator columns each: an epilogue warp is a chain of dependent
+        // TMEM loads, packed adds, conversions and a shared-memory transpose, so one warp per scheduler ran at a fraction of
+        // an instruction per clock while the MMA warp waited for TMEM (4.6 us per tile); two per scheduler overlap.
         const int q = warp & 3;
-        const int e = threadIdx.x - 64;            // 0..127
-        unsigned char* mine = staging + (size_t)q * 2 * SLAB_BYTES;
+        const int e = threadIdx.x - 64;            // 0 .. 32 * EPI_WARPS - 1
+        constexpr int SLABS = BN / EPI_COLS / (EPI_WARPS / 4);   // slabs of 16 columns per warp
+        const int c_first = ((warp - 2) >> 2) * SLABS;
+        unsigned char* mine = staging + (size_t)(warp - 2) * 2 * SLAB_BYTES;
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, lt++) {
             const int n0 = (tile % g.n_tiles) * BN, m0 = (tile / g.n_tiles) * BM;
             const int m = m0 + 32 * q + lane;
-            const float bias_mine = (kFinal && n0 + e >= g.n_valid) ? 0.f : __ldg(&g.bias[n0 + e]);
+            const float bias_mine = (e >= BN || (kFinal && n0 + e >= g.n_valid)) ? 0.f : __ldg(&g.bias[n0 + e]);
             epi_bar_sync();                        // everybody is done with the previous tile's bias
-            bias_s[e] = bias_mine;
+            if (e < BN) bias_s[e] = bias_mine;
             epi_bar_sync();
             unsigned long long* tr = (g.trace && e == 0) ? g.trace + 8 * (size_t)tile : nullptr;
             (void)tr;
@@ -328,19 +337,20 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // slabs of 16 accumulator columns, software-pipelined: slab c + 1 is in flight while slab c is processed
             uint32_t v[2][4][16];
-            tmem_load_slab(v[0], tmem_d, q, 0);
+            tmem_load_slab(v[0], tmem_d, q, c_first);
 #pragma unroll
-            for (int c = 0; c < BN / EPI_COLS; c++) {
+            for (int cc = 0; cc < SLABS; cc++) {
+                const int c = c_first + cc;        // (SLABS is even: c and cc have the same parity)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 1 < BN / EPI_COLS) {
-                    tmem_load_slab(v[(c + 1) & 1], tmem_d, q, c + 1);
+                if (cc + 1 < SLABS) {
+                    tmem_load_slab(v[(cc + 1) & 1], tmem_d, q, c + 1);
                 } else {                           // last slab is in registers: hand TMEM back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar);
                     TC_STAMP(tr, 5);
                 }
-                const uint32_t (&w)[4][16] = v[c & 1];
+                const uint32_t (&w)[4][16] = v[cc & 1];
                 const int o0 = n0 + c * EPI_COLS;
                 float x[16];
 #pragma unroll
@@ -363,16 +373,16 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     uint32_t hp[8], lp[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) split_f16x2(fmaxf(x[j], 0.f), fmaxf(x[j + 1], 0.f), hp[j >> 1], lp[j >> 1]);
-                    if ((c & 1) == 0) __syncwarp();   // the previous pair of slabs has been read out
+                    if ((cc & 1) == 0) __syncwarp();   // the previous pair of slabs has been read out
                     const int fw = (lane >> 1) & 3;
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
-                        const int chunk = 2 * (c & 1) + j;
+                        const int chunk = 2 * (cc & 1) + j;
                         *reinterpret_cast<uint4*>(mine + lane * 64 + ((chunk ^ fw) << 4)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
                         *reinterpret_cast<uint4*>(mine + SLAB_BYTES + lane * 64 + ((chunk ^ fw) << 4)) =
                             make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
                     }
-                    if (c & 1) {
+                    if (cc & 1) {
                         __syncwarp();
                         __half* oh = reinterpret_cast<__half*>(g.out_hi);
                         __half* ol = reinterpret_cast<__half*>(g.out_lo);

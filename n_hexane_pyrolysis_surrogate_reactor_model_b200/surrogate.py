@@ -32,9 +32,10 @@ TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eo
 # (rtol, atol) at which bench.py runs the explicit fast paths.  Coupled path (bs23): the loosest pair measured to keep EVERY one of
 # 65 536 sampled LHS conditions within 1e-6 of the tight-tolerance solution (max 5.8e-7): the trace species that
 # sit at 1e-6 ... 1e-3 mol/m3 are governed by atol, everything else by rtol, so the two are set separately.
-FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-7)}
+FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "taylor4": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-7)}
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
-           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP}
+           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP,
+           "taylor4": _lib.METHOD_TAYLOR4}
 
 
 def _ptr(t):
@@ -308,7 +309,7 @@ class Surrogate:
                                             _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
         res = SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
-        if method in ("bs23", "bs23w", "dp54") and stiff_fallback:
+        if method in ("bs23", "bs23w", "taylor4", "dp54") and stiff_fallback:
             # The explicit fast paths stop a condition whose steps turn out stability-limited with PFR_ST_STIFF; those conditions
             # (none for the shipped parameter sets) are integrated again, from the inlet, with the Rosenbrock kernel and their
             # results written over the flagged entries.  List and count stay on the device (pfr_stiff_fallback): no host sync.
@@ -387,7 +388,7 @@ class Surrogate:
             default_tol = FAST_TOLERANCE[method]
         rtol = default_tol[0] if rtol is None else rtol
         atol = default_tol[1] if atol is None else atol
-        pipeline_methods = ("bs23", "ros3", "rodas4") if self.energy_on else ("dp54", "ros3", "rodas4")
+        pipeline_methods = ("bs23", "taylor4", "ros3", "rodas4") if self.energy_on else ("dp54", "ros3", "rodas4")
         if staged is None:
             staged = keep_grids or method not in pipeline_methods or not sort or (not self.energy_on and L is None)
         if not staged:

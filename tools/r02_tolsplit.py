@@ -36,15 +36,16 @@ def main():
     pairs = ((1e-8, 1e-8), (1e-7, 1e-9), (1e-7, 1e-10), (1e-8, 1e-10), (1e-8, 1e-11), (1e-7, 1e-11), (1e-8, 1e-12), (1e-9, 1e-11), (1e-6, 1e-10), (1e-6, 1e-11))
     if len(sys.argv) > 4:
         pairs = tuple(tuple(float(v) for v in pr.split(":")) for pr in sys.argv[4].split(","))
-    for rtol, atol in pairs:
-        ms, res = timed(lambda: s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, method="bs23", rtol=rtol, atol=atol))
-        y = s.integrate(T[sel], c0[sel], method="bs23", rtol=rtol, atol=atol, **sub).y
+    methods = os.environ.get("PFR_TS_METHODS", "bs23").split(",")
+    for method, (rtol, atol) in ((m, pr) for pr in pairs for m in methods):
+        ms, res = timed(lambda: s.integrate(T, c0, tgrid=tfull, Tprof=Tp, idx_end=idx, perm=perm, method=method, rtol=rtol, atol=atol))
+        y = s.integrate(T[sel], c0[sel], method=method, rtol=rtol, atol=atol, **sub).y
         ee = (y - ref).abs() / torch.clamp(ref.abs(), min=1e-3)
         e = ee.amax(0)
         worst = int(e.argmax())
         sp = int(ee[:, worst].argmax())
         st = res.stats.double()
-        print(json.dumps(dict(tag=tag, mech=mech, exp="rtol_atol", rtol=rtol, atol=atol, ms=ms, attempts=float((st[0] + st[1]).mean()),
+        print(json.dumps(dict(tag=tag, mech=mech, exp="rtol_atol", method=method, rtol=rtol, atol=atol, ms=ms, evaluations=float(st[2].mean()), attempts=float((st[0] + st[1]).mean()),
                               failed=int((res.status != 0).sum()), err_max=float(e.max()), err_p99=float(torch.quantile(e, 0.99)),
                               err_median=float(e.median()), n_over_1e6=int((e > 1e-6).sum()), worst_species=sp, worst_ref=float(ref[sp, worst]),
                               worst_abs=float((y - ref)[sp, worst]))), flush=True)
