@@ -87,7 +87,7 @@ MLP_MODES = {"fp32": 0, "tf32x3": 1, "f16x3": 2}
 class MlpModel:
     """Device-side handle of one 512-wide predictor MLP (pfr_mlp_create); weights are uploaded once."""
 
-    def __init__(self, params: MLPParams, mode: str = "tf32x3"):
+    def __init__(self, params: MLPParams, mode: str = "f16x3"):
         self.params = params
         self.in_dim = params.in_dim
         W = (_lib.c_float_p * 4)(*[a.ctypes.data_as(_lib.c_float_p) for a in params.w])
@@ -147,7 +147,7 @@ class Surrogate:
     """One model variant (CRNN + time MLP [+ temperature MLP]) resident on one GPU."""
 
     def __init__(self, models: ModelSet, device: str | torch.device = "cuda", clamps=INFERENCE_CLAMPS, chunk: int = 0,
-                 mlp_mode: str = "tf32x3"):
+                 mlp_mode: str = "f16x3"):
         if not torch.cuda.is_available():
             raise _lib.PfrError("no CUDA device: this package has no CPU path")
         self.device = torch.device(device)

@@ -64,7 +64,7 @@ def surrogates(model_sets):
 
     cache = {}
 
-    def get(mech="LLNL", variant="Eoff", crnn_key=None, mlp_mode="tf32x3"):
+    def get(mech="LLNL", variant="Eoff", crnn_key=None, mlp_mode="f16x3"):
         key = (mech, variant, crnn_key, mlp_mode)
         if key not in cache:
             cache[key] = Surrogate(model_sets(mech, variant, crnn_key), mlp_mode=mlp_mode)

@@ -95,3 +95,45 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU", ""), os.path.join(dirpath, f)
+
+
+def test_sass_of_the_built_library_uses_the_hardware_paths_the_design_claims():
+    """Static evidence from the shipped binary (cuobjdump, no GPU needed).  Two properties of the build are decided by ptxas, not by
+    the source, so they are pinned here: (1) the explicit integrators feed their CRNN coefficients through UNIFORM registers (LDCU.64
+    + DFMA R, R, UR, R) -- ptxas falls back to per-thread constant loads (LDC.64 with a vector-register index) as soon as it loses
+    track of the warp being converged or of the copy index being uniform, which costs 15 % of the kernel; (2) the predictor MLPs run
+    on tcgen05 (UTCHMMA) with TMA loads and TMEM read-back, in both operand formats."""
+    import shutil
+    import subprocess
+    import pytest
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.build import LIB, build
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    build()
+    sass = subprocess.run([exe, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    per = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per[name] = {}
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and name:
+            op = m.group(1)
+            per[name][op] = per[name].get(op, 0) + 1
+
+    def count(kernel_substrings, op_prefix):
+        ks = [k for k in per if all(sub in k for sub in kernel_substrings)]
+        assert ks, kernel_substrings
+        return min(sum(v for o, v in per[k].items() if o.startswith(op_prefix)) for k in ks)
+
+    for kern in (["bs23_kernelId"], ["dp54_kernelId"]):
+        assert count(kern, "LDCU.64") >= 162, (kern, "coefficient loads are not uniform-register loads")
+        ks = [k for k in per if kern[0] in k]
+        assert max(per[k].get("LDC.64", 0) for k in ks) < 40, (kern, "per-thread constant loads")
+    for fmt in ("ILb0ELb0E", "ILb0ELb1E", "ILb1ELb0E", "ILb1ELb1E"):   # <kFinal, kHalf>
+        kern = ["mlp_tc_gemm_kernel", fmt]
+        assert count(kern, "UTCHMMA") >= 12 and count(kern, "UTMALDG") >= 4 and count(kern, "LDTM") >= 8

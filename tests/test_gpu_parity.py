@@ -550,7 +550,42 @@ def test_sweep_sorted_equals_unsorted(surrogates, conditions):
     assert torch.equal(a.y, b.y)                                # the permutation only reorders threads
 
 
-@pytest.mark.parametrize("method,precision", [("rodas4", 64), ("rodas4", 32), ("rodas4_tpc", 64), ("dopri5", 32), ("ros3", 64), ("bs23", 64), ("bs23", 32)])
+@pytest.mark.parametrize("variant", ["Eoff", "Eon"])
+def test_taylor4_vs_converged_truth_golden(surrogates, golden, variant):
+    """The Taylor-series integrator (PFR_METHOD_TAYLOR4: time derivatives of f = W exp(kT + nu^T ln y) from the series recurrences of log
+    and exp, steps cut where a species crosses the lower state clamp) converges to the same solution as every other integrator: within
+    1e-6 of the converged oracle solution at the bench tolerance (rtol 3e-7, atol 1e-12), outlet and every 50th knot of the dense
+    output, isothermal and on the temperature ramp; one coefficient evaluation per attempt; no more attempts than BS23 at the same
+    tolerance; its float32 instantiation stays within the float32 envelope of the other kernels."""
+    s = surrogates("LLNL", variant)
+    tg, Tp, idx = _grids(golden, variant)
+    tgd = torch.as_tensor(tg.T.copy()).cuda()
+    Tpd = torch.as_tensor(Tp.T.copy()).cuda() if variant == "Eon" else None
+    idxd = torch.as_tensor(idx).cuda() if variant == "Eon" else None
+    kw = dict(tgrid=tgd, Tprof=Tpd, idx_end=idxd)
+    truth = np.clip(golden[f"{variant}/truth_outlet"], 1e-6, 60.0)
+    r = s.integrate(golden["T"], golden["c0"][:, 6], method="taylor4", rtol=3e-7, atol=1e-12, dense=True, stiff_fallback=None, **kw)
+    assert int(r.status.abs().sum()) == 0
+    st = r.stats.cpu().numpy()
+    assert np.array_equal(st[2], st[0] + st[1])
+    e = np.max(rel_err(r.y.cpu().numpy().T, truth))
+    assert e < 1e-6, e
+    dense = r.dense.cpu().numpy()
+    for j, k in enumerate(range(0, 801, 50)):
+        ok = k <= idx
+        if ok.any():
+            ref = np.clip(golden[f"{variant}/truth_knots_every50"][ok, j, :], 1e-6, 60.0)
+            assert np.max(rel_err(dense[k][:, ok].T, ref)) < 1e-6
+    b = s.integrate(golden["T"], golden["c0"][:, 6], method="bs23", rtol=3e-7, atol=1e-12, stiff_fallback=None, **kw)
+    sb = b.stats.cpu().numpy()
+    assert (st[0] + st[1]).mean() <= (sb[0] + sb[1]).mean() + 8        # (+ the few steps cut at clamp crossings)
+    f32 = s.integrate(golden["T"], golden["c0"][:, 6], method="taylor4", precision=32, rtol=1e-5, atol=1e-7, **kw)
+    assert int(f32.status.abs().sum()) == 0 and np.max(rel_err(f32.y.double().cpu().numpy().T, truth)) < 5e-3
+    print(f"taylor4 {variant}: {e:.2e}, attempts {(st[0] + st[1]).mean():.0f} (bs23 {(sb[0] + sb[1]).mean():.0f})")
+
+
+@pytest.mark.parametrize("method,precision", [("rodas4", 64), ("rodas4", 32), ("rodas4_tpc", 64), ("dopri5", 32), ("ros3", 64), ("bs23", 64), ("bs23", 32),
+                                              ("taylor4", 64), ("taylor4", 32)])
 def test_integrators_ragged_batch_sizes(surrogates, conditions, method, precision):
     """Batches that do not fill a warp / a 10-condition group / a CTA: every condition is an independent problem, so
     the first n columns of a full-batch run and an n-condition run are bit-identical (Eon grids, outlet at idx_cut)."""

@@ -16,7 +16,7 @@ def _lhs(n, seed=7):
     return lhs_conditions(n, seed=seed)
 
 
-@pytest.mark.parametrize("variant,method,tol", [("Eon", "bs23", (3e-7, 1e-12)), ("Eon", "ros3", (1e-7, 1e-7)), ("Eon", "rodas4", (1e-6, 1e-6)),
+@pytest.mark.parametrize("variant,method,tol", [("Eon", "bs23", (3e-7, 1e-12)), ("Eon", "taylor4", (3e-7, 1e-12)), ("Eon", "ros3", (1e-7, 1e-7)), ("Eon", "rodas4", (1e-6, 1e-6)),
                                                 ("Eoff", "dp54", (1e-7, 1e-7)), ("Eoff", "rodas4", (1e-6, 1e-6))])
 @pytest.mark.parametrize("n", [1, 257, 5000])
 def test_one_call_sweep_equals_staged_sweep(surrogates, variant, method, tol, n):
