@@ -236,8 +236,9 @@ int pfr_mlp_trainer_loss(pfr_mlp_trainer_t t, const float* x, const float* y, in
 int pfr_mlp_trainer_read(pfr_mlp_trainer_t t, float* const weights[4], float* const biases[4]);
 
 /* Parity hook for the table-driven double-precision log (kind 0, x positive normal) / exp (kind 1, |x| < 700)
- * used inside the Rosenbrock kernel in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).
- * x[n] -> y[n], device pointers. */
+ * used inside the integrators in place of torch.log / torch.exp of CRNNFunc.forward (...Eoff_single_model.py:139,151).
+ * kind 2 = the exponential as the explicit integrators evaluate it (exponents carried in units of ln2 / 256; the hook scales x),
+ * kind 3 / 4 = the latency-oriented log / exp of the warp-per-condition kernels.  x[n] -> y[n], device pointers. */
 int pfr_fastmath(int kind, int n, const double* x, double* y, void* stream);
 
 /* Pipe micro-benchmarks used as roofline denominators (synchronous; a few ms each).

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrnn_pfr_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["sweep_order.cuh", "adjoint_phases.cuh", "integrate_lanes.cuh", "crnn_device.cuh", "integrate_explicit.cuh", "fastmath.cuh", "integrate_rodas.cuh", "integrate_rodas_coop.cuh", "adjoint.cuh", "integrate_dopri5.cuh", "mlp.cuh", "mlp_tc.cuh", "mlp_train.cuh", "../../include/crnn_pfr.h"]
+HEADERS = ["sweep_order.cuh", "adjoint_phases.cuh", "integrate_lanes.cuh", "crnn_device.cuh", "integrate_explicit.cuh", "integrate_taylor.cuh", "fastmath.cuh", "integrate_rodas.cuh", "integrate_rodas_coop.cuh", "adjoint.cuh", "integrate_dopri5.cuh", "mlp.cuh", "mlp_tc.cuh", "mlp_train.cuh", "../../include/crnn_pfr.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",

@@ -1245,12 +1245,17 @@ extern "C" int pfr_mlp_trainer_read(pfr_mlp_trainer_t t, float* const weights[4]
 __global__ void __launch_bounds__(128) fastmath_kernel(const FastTables* __restrict__ ft, int kind, int n,
                                                        const double* __restrict__ x, double* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = kind == 0 ? fast_log(x[i], ft->logtab) : fast_exp(x[i], ft->exptab);
+    if (i < n)
+        y[i] = kind == 0   ? fast_log(x[i], ft->logtab)
+               : kind == 1 ? fast_exp(x[i], ft->exptab)
+               : kind == 2 ? fast_exp_scaled(x[i] * EXP_ARG_SCALE, ft->exptab)   // (the explicit integrators' form: argument in units of ln2 / 256)
+               : kind == 3 ? fast_log_ilp(x[i], ft->logtab)
+                           : fast_exp_ilp(x[i], ft->exptab);
 }
 
 extern "C" int pfr_fastmath(int kind, int n, const double* x, double* y, void* stream) {
     if (n == 0) return PFR_OK;
-    if (!x || !y || n < 0 || (kind != 0 && kind != 1)) return PFR_EINVAL;
+    if (!x || !y || n < 0 || kind < 0 || kind > 4) return PFR_EINVAL;
     DeviceCtx* ctx = nullptr;
     const int rc = device_ctx(&ctx);
     if (rc != PFR_OK) return rc;

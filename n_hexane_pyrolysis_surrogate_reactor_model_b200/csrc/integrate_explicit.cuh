@@ -57,6 +57,13 @@ template <> __device__ __forceinline__ float t_log<float>(float x, const FastTab
 template <typename real> __device__ __forceinline__ real t_exp(real x, const FastTables& ft);
 template <> __device__ __forceinline__ double t_exp<double>(double x, const FastTables& ft) { return fast_exp(x, ft.exptab); }
 template <> __device__ __forceinline__ float t_exp<float>(float x, const FastTables&) { return expf(x); }
+// The explicit kernels carry the exponents z_j in units of ln2 / 256 (double; plain units in float): nu, Ea, b, lnA and the exponent
+// clamp are pre-scaled once (fill_coef_dup / load_tpc_coef with kScaled), which turns the range reduction of the exponential into
+// one exact subtraction (fast_exp_scaled: 8 FP64 instructions instead of 9).
+template <typename real> __host__ __device__ constexpr real z_scale() { return sizeof(real) == 8 ? real(EXP_ARG_SCALE) : real(1); }
+template <typename real> __device__ __forceinline__ real t_exp_scaled(real x, const FastTables& ft);
+template <> __device__ __forceinline__ double t_exp_scaled<double>(double x, const FastTables& ft) { return fast_exp_scaled(x, ft.exptab); }
+template <> __device__ __forceinline__ float t_exp_scaled<float>(float x, const FastTables&) { return expf(x); }
 
 // Block-shared copy of the CRNN coefficients, laid out in the order the right-hand side consumes them.  Every thread
 // reads the same address (a broadcast), two coefficients per 16-byte load.  (As FMA operands straight from the
@@ -91,17 +98,18 @@ struct __align__(16) CoefDup {
 };
 template <typename real>
 static inline void fill_coef_dup(CoefDup<real>& d, const CrnnParams<real>& p) {
+    const real zs = z_scale<real>();   // (nu and the Arrhenius coefficients in units of ln2 / 256, see t_exp_scaled)
     for (int c = 0; c < 2; c++)
         for (int r = 0; r < NS; r++)
             for (int e = 0; e < 10; e++) {
-                d.nu[c][r][e] = e < NR ? p.nu[r][e] : real(0);
+                d.nu[c][r][e] = e < NR ? zs * p.nu[r][e] : real(0);
                 d.woutT[c][r][e] = e < NS ? p.wout[e][r] : real(0);
             }
     for (int c = 0; c < 2; c++)
         for (int j = 0; j < NR; j++) {
-            d.arr[c][j][0] = p.Ea[j];
-            d.arr[c][j][1] = p.b[j];
-            d.arr[c][j][2] = p.lnA[j];
+            d.arr[c][j][0] = zs * p.Ea[j];
+            d.arr[c][j][1] = zs * p.b[j];
+            d.arr[c][j][2] = zs * p.lnA[j];
             d.arr[c][j][3] = real(0);
         }
 }
@@ -157,6 +165,7 @@ __device__ __forceinline__ void arrhenius_uni(const CrnnParams<real>& p, const T
 template <typename real, int kUniRows>
 __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, int zthr, int dthr,
                                            const real (&kT)[NR], const real (&y)[NS], real (&du)[NS]) {
+    // (kT, nu and therefore z are in units of ln2 / 256 -- z_scale; zthr is the key of the scaled clamp bound)
     real z[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) z[j] = kT[j];
@@ -180,13 +189,13 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
     for (int j = 0; j < NR; j++) near = near || maybe_outside(z[j], zthr);
     if (near) {
 #pragma unroll
-        for (int j = 0; j < NR; j++) z[j] = m_min(m_max(z[j], p.zlo), p.zhi);
+        for (int j = 0; j < NR; j++) z[j] = m_min(m_max(z[j], z_scale<real>() * p.zlo), z_scale<real>() * p.zhi);
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) du[i] = real(0);
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-        const real r = t_exp<real>(z[j], sc.ft);
+        const real r = t_exp_scaled<real>(z[j], sc.ft);
         if ((kUniRows >> j) & 1) {
 #pragma unroll
             for (int i = 0; i < NS; i++) du[i] = fma(cd.woutT[copy][j][i], r, du[i]);
@@ -218,17 +227,18 @@ __device__ __forceinline__ void rhs_tpc(const CrnnParams<real>& p, const TpcCoef
 }
 
 // block-shared copy of the coefficients and tables (every kernel of this file starts with it)
-template <typename real, int kBlock>
+template <typename real, int kBlock, bool kScaled = false>
 __device__ __forceinline__ void load_tpc_coef(TpcCoef<real>& sc, const CrnnParams<real>& p, const FastTables* tables) {
+    const real zs = kScaled ? z_scale<real>() : real(1);   // kScaled: exponent coefficients in units of ln2 / 256 (t_exp_scaled)
     for (int e = threadIdx.x; e < NS * 10; e += kBlock) {
         const int r = e / 10, c = e % 10;
-        sc.nu[r][c] = c < NR ? p.nu[r][c] : real(0);
+        sc.nu[r][c] = c < NR ? zs * p.nu[r][c] : real(0);
         sc.woutT[r][c] = c < NS ? p.wout[c][r] : real(0);
     }
     if (threadIdx.x < NR) {
-        sc.arr[threadIdx.x][0] = p.Ea[threadIdx.x];
-        sc.arr[threadIdx.x][1] = p.b[threadIdx.x];
-        sc.arr[threadIdx.x][2] = p.lnA[threadIdx.x];
+        sc.arr[threadIdx.x][0] = zs * p.Ea[threadIdx.x];
+        sc.arr[threadIdx.x][1] = zs * p.b[threadIdx.x];
+        sc.arr[threadIdx.x][2] = zs * p.lnA[threadIdx.x];
         sc.arr[threadIdx.x][3] = real(0);
     }
     if (sizeof(real) == 8) {
@@ -242,8 +252,8 @@ template <typename real, bool kRamp>
 __global__ void __launch_bounds__(BS23_BLOCK, PFR_BS23_MINB)
 bs23_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ CoefDup<real> cd, const RodasArgs a) {
     __shared__ __align__(16) TpcCoef<real> sc;
-    load_tpc_coef<real, BS23_BLOCK>(sc, p, a.tables);
-    const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
+    load_tpc_coef<real, BS23_BLOCK, true>(sc, p, a.tables);
+    const int zthr = bound_key(z_scale<real>() * m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
     const size_t n = (size_t)a.n;
     real* __restrict__ y_out = static_cast<real*>(a.y_out);
     real* __restrict__ y_dense = static_cast<real*>(a.y_dense);
@@ -373,15 +383,13 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
             }   // k2 now holds k4 = f(t + h, y1): the next step's k1
           if (active) {
             nrhs += 3;
-            real e2 = real(0), d0 = real(0), d1 = real(0);
+            real e2 = real(0);
             bool finite = true;
 #pragma unroll
             for (int k = 0; k < NS; k++) {
                 const real ek = h * fma(real(-1.0 / 8.0), k2[k], ER(k));
                 const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
                 e2 = fma(ek * isk, ek * isk, e2);
-                d0 = fma(y[k] * isk, y[k] * isk, d0);     // only used by a fresh condition (first-step guess)
-                d1 = fma(k2[k] * isk, k2[k] * isk, d1);
                 finite = finite && (m_abs(w[k]) < real(1e30));
             }
             real err = m_sqrt<real>(e2 / real(NS));
@@ -401,6 +409,13 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
                 // the zero-length step left y unchanged and k2 = f(t0, y0); Hairer-style first step from |y0| and |f0|
 #pragma unroll
                 for (int k = 0; k < NS; k++) K1(k) = k2[k];
+                real d0 = real(0), d1 = real(0);   // (once per trajectory: kept out of the per-step norm, 36 FP64 instructions)
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const real isk = rcp_norm(atol + rtol * m_abs(y[k]));   // (w = y after the zero-length step)
+                    d0 = fma(y[k] * isk, y[k] * isk, d0);
+                    d1 = fma(k2[k] * isk, k2[k] * isk, d1);
+                }
                 d0 = m_sqrt<real>(d0 / real(NS));
                 d1 = m_sqrt<real>(d1 / real(NS));
                 const double h0 = (d0 < real(1e-5) || d1 < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
@@ -516,8 +531,8 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
     __shared__ __align__(16) TpcCoef<real> sc;
     extern __shared__ __align__(16) unsigned char dp_dyn[];
     real* const ks = reinterpret_cast<real*>(dp_dyn) + threadIdx.x;   // slope k_s of species i: ks[(s * NS + i) * DP54_BLOCK]
-    load_tpc_coef<real, DP54_BLOCK>(sc, p, a.tables);
-    const int zthr = bound_key(m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
+    load_tpc_coef<real, DP54_BLOCK, true>(sc, p, a.tables);
+    const int zthr = bound_key(z_scale<real>() * m_min(m_abs(p.zlo), m_abs(p.zhi))), dthr = bound_key(m_min(m_abs(p.dulo), m_abs(p.duhi)));
     const size_t n = (size_t)a.n;
     real* __restrict__ y_out = static_cast<real*>(a.y_out);
     const real rtol = real(a.rtol), atol = real(a.atol);
@@ -589,7 +604,7 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
           if (active) {
             nrhs += fresh ? 1 : DP54_STAGES - 1;
             // w = y1 (row 6 of the tableau = the 5th-order weights), f = f(y1)   [entry step: w = y0, f = f(y0), h = 0]
-            real e2 = real(0), d0 = real(0), d1 = real(0);
+            real e2 = real(0);
             bool finite = true;
 #pragma unroll
             for (int k = 0; k < NS; k++) {
@@ -599,8 +614,6 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
                 ek *= h;
                 const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
                 e2 = fma(ek * isk, ek * isk, e2);
-                d0 = fma(y[k] * isk, y[k] * isk, d0);
-                d1 = fma(f[k] * isk, f[k] * isk, d1);
                 finite = finite && (m_abs(w[k]) < real(1e30));
             }
             real err = m_sqrt<real>(e2 / real(NS));
@@ -614,6 +627,13 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
             finite = finite && (err == err) && (err < real(1e30));
             const float fac = 0.9f * __powf(fmaxf((float)err, 1e-30f), -0.2f);
             if (fresh) {
+                real d0 = real(0), d1 = real(0);   // (once per trajectory: kept out of the per-step norm)
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const real isk = rcp_norm(atol + rtol * m_abs(y[k]));   // (w = y on the entry step)
+                    d0 = fma(y[k] * isk, y[k] * isk, d0);
+                    d1 = fma(f[k] * isk, f[k] * isk, d1);
+                }
                 d0 = m_sqrt<real>(d0 / real(NS));
                 d1 = m_sqrt<real>(d1 / real(NS));
                 const double h0 = (d0 < real(1e-5) || d1 < real(1e-5)) ? 1e-6 : 0.01 * (double)d0 / (double)d1;

@@ -506,10 +506,12 @@ class Surrogate:
 
 
 def fastmath(kind: str, x: torch.Tensor) -> torch.Tensor:
-    """The kernel's table-driven float64 log / exp on a CUDA tensor (parity hook)."""
+    """The kernels' table-driven float64 log / exp on a CUDA tensor (parity hook): 'log', 'exp', 'exp_scaled' (the explicit
+    integrators' form, which takes its argument pre-multiplied by 256 / ln 2 -- the hook multiplies), 'log_ilp', 'exp_ilp' (the
+    latency-oriented variants of the warp-per-condition kernels)."""
     x = x.to(dtype=torch.float64).contiguous()
     y = torch.empty_like(x)
-    _lib.check(_lib.lib().pfr_fastmath({"log": 0, "exp": 1}[kind], x.numel(), _ptr(x), _ptr(y), _stream()), "pfr_fastmath")
+    _lib.check(_lib.lib().pfr_fastmath({"log": 0, "exp": 1, "exp_scaled": 2, "log_ilp": 3, "exp_ilp": 4}[kind], x.numel(), _ptr(x), _ptr(y), _stream()), "pfr_fastmath")
     return y
 
 

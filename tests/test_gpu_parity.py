@@ -55,22 +55,27 @@ def test_rhs_golden_anchor(surrogates, golden):
 
 
 def test_fast_log_exp(surrogates):
-    """The table-driven float64 log / exp of the Rosenbrock kernel vs numpy (glibc, < 1 ulp): exp within 2 ulp of
-    the result, log within 2.5e-15 absolute over the clamped state range (1 ulp at |log| ~ 14) and within 4 ulp of
-    the result away from log ~ 0."""
+    """The table-driven float64 log / exp of the integrators vs numpy (glibc, < 1 ulp), every variant the kernels use (the plain
+    ones, the latency-oriented ones of the warp-per-condition kernels, and the exponential that takes its argument in units of
+    ln2 / 256 inside the explicit integrators): exp within 2 ulp of the result; log within 3e-15 absolute over the clamped state
+    range (1.5 ulp at |log| ~ 14) -- the right-hand side adds nu * log y into an exponent, so the absolute error is the one that
+    matters -- and within 1.5e-15 of max(|log|, 1) (the degree-4 minimax polynomial on |r| <= 2^-9 leaves 7.4e-16)."""
     from n_hexane_pyrolysis_surrogate_reactor_model_b200.surrogate import fastmath
     surrogates()
     rng = np.random.default_rng(3)
     x = np.concatenate([np.exp(rng.uniform(np.log(1e-6), np.log(60.0), 200000)), rng.uniform(0.5, 2.0, 50000),
-                        rng.uniform(300.0, 3000.0, 50000), [1e-6, 60.0, 1.0, 2.0, 0.5]])
-    got = fastmath("log", torch.as_tensor(x).cuda()).cpu().numpy()
+                        rng.uniform(300.0, 3000.0, 50000), 1.0 + np.arange(0, 257) / 256.0, [1e-6, 60.0, 1.0, 2.0, 0.5]])
     ref = np.log(x)
-    assert np.max(np.abs(got - ref)) < 2.5e-15
-    big = np.abs(ref) > 0.05
-    assert np.max(np.abs(got - ref)[big] / np.abs(ref[big])) < 9e-16
+    for kind in ("log", "log_ilp"):
+        got = fastmath(kind, torch.as_tensor(x).cuda()).cpu().numpy()
+        assert np.max(np.abs(got - ref)) < 3e-15, kind
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1.5e-15, kind
     z = np.concatenate([rng.uniform(-30.0, 30.0, 300000), [-30.0, 30.0, 0.0, -1e-300, 700.0, -700.0]])
-    got = fastmath("exp", torch.as_tensor(z).cuda()).cpu().numpy()
-    assert np.max(np.abs(got - np.exp(z)) / np.exp(z)) < 4.5e-16
+    for kind in ("exp", "exp_ilp", "exp_scaled"):
+        got = fastmath(kind, torch.as_tensor(z).cuda()).cpu().numpy()
+        # (the scaled form rounds its argument once more: x * 256 / ln 2 carries half an ulp of x, i.e. up to |x| 2^-53 relative)
+        bound = 4.5e-16 + (np.abs(z) * 2.3e-16 if kind == "exp_scaled" else 0.0)
+        assert np.all(np.abs(got - np.exp(z)) / np.exp(z) < bound), kind
 
 
 def test_rodas_three_lane_kernel_equals_thread_per_condition(surrogates, conditions):
