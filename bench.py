@@ -35,13 +35,17 @@ METRIC = "PFR trajectories/sec (1M LHS conditions)"
 # that owned a whole condition would have to execute with the kernel's own log/exp (fastmath.cuh); 1 instruction
 # = 2 flop, so achieved / measured-DFMA-peak is the FP64-pipe utilisation a redundancy-free schedule would show.
 # The 3-lane kernel executes ~35 % more than this (replicated control flow, Gauss-Jordan instead of LU).
-FP64_LOG, FP64_EXP, FP64_RCP = 11, 10, 5                      # table-driven log / exp, MUFU.RCP64H + 2 Newton steps
+FP64_LOG, FP64_EXP, FP64_RCP = 8, 9, 5                        # table-driven log / exp (256-entry tables, degree 4), MUFU.RCP64H + 2 Newton steps
 FP64_RHS = 2 * 81 + 9 * FP64_LOG + 9 * FP64_EXP + 27           # two 9x9 mat-vecs, 9 log + 9 exp, clamp compares
 FP64_RHS_T = FP64_LOG + FP64_RCP + 27                          # on a T ramp: ln T, 1/T, kT_j = lnA - Ea/RT + b lnT
+# the explicit kernels (bs23 / dp54): exponents pre-scaled (exp = 8 instructions), only the state clamp compares on the FP64 pipe
+# (18 DSETP; the exponent / output clamps are decided on the integer pipe), kT_j as two FMAs per reaction
+FP64_RHS_EXPL = 2 * 81 + 9 * FP64_LOG + 9 * 8 + 18
+FP64_RHS_T_EXPL = FP64_LOG + FP64_RCP + 19
 FP64_STEP = (81 + 729 + 81) + (204 + 36 + 9 * FP64_RCP) + 6 * 81 + (90 + 18 + 135 + 15) + 50   # J, LU, 6 solves, stage sums, norm
 FP64_STEP_ROS3 = (81 + 729 + 81) + (204 + 36 + 9 * FP64_RCP) + 3 * 81 + 108 + 50                # J, LU, 3 solves, stage sums, norm
-FP64_STEP_BS23 = 18 + 36 + 27 + 18 + 63                                                        # stage arguments, solution, error combination, norm
-FP64_STEP_DP54 = 9 * (21 + 6 + 7 + 8)                                                          # stage arguments, error combination, norm
+FP64_STEP_BS23 = 9 + 45 + 27 + 63                                                              # stage arguments / solution / error combinations of the three stages, norm
+FP64_STEP_DP54 = 9 * (21 + 6 + 7 + 4)                                                          # stage arguments, error combination, norm
 # Taylor-4: one coefficient evaluation = one log / exp set, eight mat-vecs, the kT series terms, 1/Y, the log / exp series recurrences
 FP64_TAYLOR4_EVAL = 8 * 81 + 9 * FP64_LOG + 9 * FP64_EXP + 27 + 54 + 27 + 198
 FP64_STEP_TAYLOR4 = 36 + 63                                                                      # Horner, error norm
@@ -115,8 +119,10 @@ def _flops(stats, energy_on, method="rodas4"):
     """Algorithmic FP64 work of one integrator launch from its per-trajectory counters [3, n]."""
     import torch
     acc, rej, rhs = (stats[i].to(torch.float64).sum().item() for i in range(3))
-    per_rhs = FP64_TAYLOR4_EVAL if method == "taylor4" else FP64_RHS
-    instr = rhs * (per_rhs + (FP64_RHS_T if energy_on else 0)) + (acc + rej) * STEP_INSTR[method]
+    explicit = method in ("bs23", "dp54")
+    per_rhs = FP64_TAYLOR4_EVAL if method == "taylor4" else (FP64_RHS_EXPL if explicit else FP64_RHS)
+    per_rhs_t = FP64_RHS_T_EXPL if explicit else FP64_RHS_T
+    instr = rhs * (per_rhs + (per_rhs_t if energy_on else 0)) + (acc + rej) * STEP_INSTR[method]
     return 2.0 * instr, {"accepted_mean": acc / stats.shape[1], "rejected_mean": rej / stats.shape[1], "rhs_mean": rhs / stats.shape[1]}
 
 
@@ -346,8 +352,11 @@ def run_ours(args, emit=print):
                      "traffic_source": "derived in this run from the outlet knots walked (inputs 12 B, 8 B per knot up to idx_cut + 2, results 88 B); "
                                        "ncu on the same kernel: 4.21 KB per condition, L2 hit rate 71 % (profiles/r02b_ncu_full_bs23_dp54_fp64.txt; "
                                        "round 1, reads gathered through a permutation: 74.8 KB)",
-                     "flop_model": f"2 flop per FP64-pipe instruction of the algorithm: RHS {FP64_RHS} (+{FP64_RHS_T} on a T ramp), "
-                                   f"BS23 step overhead {FP64_STEP_BS23} (stage sums, error norm; ROS3: {FP64_STEP_ROS3}, RODAS4: {FP64_STEP}); see DESIGN.md"},
+                     "flop_model": f"2 flop per FP64-pipe instruction of the algorithm as shipped: RHS {FP64_RHS_EXPL} (+{FP64_RHS_T_EXPL} on a T ramp; "
+                                   f"two 9x9 mat-vecs, 9 log + 9 exp at 8 instructions each, 18 clamp compares), BS23 step overhead {FP64_STEP_BS23} "
+                                   f"(stage sums, error norm); the Rosenbrock variants: RHS {FP64_RHS} (+{FP64_RHS_T}), step ROS3 {FP64_STEP_ROS3}, "
+                                   f"RODAS4 {FP64_STEP}; see DESIGN.md. (Round 1 / the first half of round 2 counted 421 (+43) per RHS: the log / exp "
+                                   f"were 11 + 10 instructions then, so fractions across rounds compare pipe utilisation, not speed.)"},
         "accuracy": accuracy,
         "peaks_measured": {"ffma_tflops": peaks["ffma_flops"] / 1e12, "dfma_tflops": peaks["dfma_flops"] / 1e12, "mufu_tops": peaks["mufu_ops"] / 1e12},
         "variants": variants,

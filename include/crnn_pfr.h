@@ -34,7 +34,7 @@ extern "C" {
 #define PFR_ST_MAXSTEPS 1
 #define PFR_ST_NONFINITE 2
 #define PFR_ST_UNDERFLOW 3
-#define PFR_ST_STIFF 4      /* explicit fast paths only (PFR_METHOD_BS23, _BS23_WARP, _DP54): the explicit fast path met a stiff knot interval; integrate this condition with
+#define PFR_ST_STIFF 4      /* explicit fast paths only (PFR_METHOD_BS23, _BS23_WARP, _DP54, _DP54_WARP): the explicit fast path met a stiff knot interval; integrate this condition with
                             * PFR_METHOD_ROS3 / PFR_METHOD_RODAS4 (Surrogate does so automatically) */
 
 #define PFR_FLAG_DENSE_RAW 1
@@ -55,6 +55,10 @@ extern "C" {
 #define PFR_METHOD_BS23_WARP 6  /* PFR_METHOD_BS23 with ONE CONDITION PER WARP (lane = species = reaction; float64, tgrid required): the
                                  * latency-oriented mapping for batches of a few hundred conditions with dense output -- the forward
                                  * pass of the training step; same method and controller, dot products summed in another order */
+#define PFR_METHOD_DP54_WARP 8  /* Dormand-Prince 5(4) with ONE CONDITION PER WARP, free stepping along tgrid's time span at T = T0 (tgrid required,
+                                 * Tprof must be NULL, float64), y_dense from the method's 4th-order continuous extension at the 801 knots -- what
+                                 * torchdiffeq's dopri5 does for the reference's isothermal trainers (...WIDE_Eoff_surrogate_model_training.py:383):
+                                 * the forward pass of the isothermal training step, ~30-60 steps instead of 800; PFR_ST_STIFF as for DP54 */
 #define PFR_METHOD_TAYLOR4 7    /* explicit Taylor-series method of order 4 (3), one thread per condition, knot-limited (tgrid required): the time
                                  * derivatives of f = W exp(kT + nu^T ln y) come from the series recurrences of log and exp, so a step costs ONE
                                  * set of logarithms / exponentials and eight 9x9 mat-vecs instead of BS23's three right-hand sides; steps are cut

@@ -16,6 +16,7 @@ METHOD_ROS3 = 3
 METHOD_BS23 = 4
 METHOD_DP54 = 5
 METHOD_BS23_WARP = 6
+METHOD_DP54_WARP = 8
 METHOD_TAYLOR4 = 7
 ST_STIFF = 4
 SWEEP_NO_ORDER, SWEEP_NO_FALLBACK = 1, 2

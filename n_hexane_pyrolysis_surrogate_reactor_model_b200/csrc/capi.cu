@@ -745,6 +745,12 @@ static int integrate_launch(DeviceCtx& ctx, crnn_model_t m, int method, int prec
             CK_LAUNCH("bs23_lanes_kernel");
             return PFR_OK;
         }
+        case PFR_METHOD_DP54_WARP: {
+            if (!d || a.Tprof) return PFR_EINVAL;
+            dp54_lanes_kernel<<<(a.n + LANES_WARPS - 1) / LANES_WARPS, 32 * LANES_WARPS, 0, st>>>(m->pd, a);
+            CK_LAUNCH("dp54_lanes_kernel");
+            return PFR_OK;
+        }
         case PFR_METHOD_RODAS4_TPC: return d ? dispatch_rodas<double>(m->pd, a, st) : dispatch_rodas<float>(m->pf, a, st);
         case PFR_METHOD_DOPRI5: {
             Dopri5Args da{a.n, a.T0, a.c0, a.tgrid, a.Tprof, a.t_end, a.idx_end, a.perm, a.rtol, a.atol, a.y_out, a.y_dense, a.status, a.stats, a.max_steps};
@@ -761,9 +767,11 @@ extern "C" int pfr_integrate(crnn_model_t m, int method, int precision, int n, c
     if (!m || !T0 || !c0 || !y_out || !status || n < 0) return PFR_EINVAL;
     if (precision != 32 && precision != 64) return PFR_EINVAL;
     if (method != PFR_METHOD_RODAS4 && method != PFR_METHOD_DOPRI5 && method != PFR_METHOD_RODAS4_TPC && method != PFR_METHOD_ROS3 &&
-        method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54 && method != PFR_METHOD_BS23_WARP && method != PFR_METHOD_TAYLOR4)
+        method != PFR_METHOD_BS23 && method != PFR_METHOD_DP54 && method != PFR_METHOD_BS23_WARP && method != PFR_METHOD_TAYLOR4 &&
+        method != PFR_METHOD_DP54_WARP)
         return PFR_EINVAL;
     if (method == PFR_METHOD_BS23_WARP && (!tgrid || precision != 64)) return PFR_EINVAL;   // knot-limited, float64 state
+    if (method == PFR_METHOD_DP54_WARP && (!tgrid || Tprof || precision != 64)) return PFR_EINVAL;   // isothermal, outputs at tgrid's knots, float64
     if (method == PFR_METHOD_DP54 && (tgrid || !t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;   // isothermal outlet at t_end only
     if ((method == PFR_METHOD_BS23 || method == PFR_METHOD_TAYLOR4) && !tgrid) return PFR_EINVAL;   // the explicit fast paths are knot-limited steppers
     if (!tgrid && (!t_end || Tprof || y_dense || idx_end)) return PFR_EINVAL;

@@ -60,7 +60,12 @@ __device__ __forceinline__ double fast_log(double x, const double2* __restrict__
 // exponent adjustment 2^q applied to the high word
 __device__ __forceinline__ double exp_finish(double T, double p, int k) {
     const double res = fma(T, p, T);
-    return __hiloint2double(__double2hiint(res) + ((k >> EXPTAB_BITS) << 20), __double2loint(res));
+    // 2^q with q = k >> 8 into the exponent field: (k with its table index cleared) << 12, one mask and one shift-add (LEA)
+    // (written as a multiply-add so that it stays ONE integer instruction behind the mask: the compiler's own form of
+    // ((k >> 8) << 20) + hi is shift, mask, add)
+    int hi;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(k & ~(EXPTAB_N - 1)), "n"(1 << (20 - EXPTAB_BITS)), "r"(__double2hiint(res)));
+    return __hiloint2double(hi, __double2loint(res));
 }
 
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {

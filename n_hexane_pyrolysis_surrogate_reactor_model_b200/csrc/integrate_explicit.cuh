@@ -23,8 +23,9 @@
 // wasted work: at most ~3x the cost of the Rosenbrock integration it falls back to.)  The
 // product stays an adaptive stiff-capable integrator; this is its fast path.
 //
-// Same controller conventions as the Rosenbrock kernels: RMS norm against atol + rtol max(|y0|, |y1|), Hairer-style
-// first step, factor clip(0.9 err^(-1/3), 0.2, 6), a knot-clipped accepted step does not shrink the proposal.
+// Same controller conventions as the Rosenbrock kernels (RMS norm against atol + rtol max(|y0|, |y1|) -- bs23 weighs with |y1|
+// alone, PFR_NORM_NEW_ONLY --, Hairer-style first step, factor clip(0.9 err^(-1/3), 0.2, 6)); a knot-clipped accepted step does
+// not shrink the proposal.
 #pragma once
 #include "crnn_device.cuh"
 #include "fastmath.cuh"
@@ -37,14 +38,21 @@ namespace pfr {
                                 // registers: 252 -> 168 registers without spills, i.e. three CTAs per SM; measured 84.5 -> 78.4 ms
                                 // for 2^20 conditions at 1e-8 (with two CTAs the shared-memory version is 4 % slower than registers)
 #endif
-template <typename real> constexpr size_t bs23_smem_bytes() { return PFR_BS23_SMEM_STATE ? (size_t)3 * NS * 128 * sizeof(real) : 0; }
+#ifndef PFR_BS23_BLOCK
+#define PFR_BS23_BLOCK 128
+#endif
+template <typename real> constexpr size_t bs23_smem_bytes() { return PFR_BS23_SMEM_STATE ? (size_t)3 * NS * PFR_BS23_BLOCK * sizeof(real) : 0; }
 #ifndef PFR_BS23_KINK
 #define PFR_BS23_KINK 0     // error margin demanded of a step that straddles the kink of the lower state clamp; 0 = off.
                             // Measured with 100 (2^20 LHS conditions, 1e-8): median outlet error 2.1e-7 -> 6.1e-8, p99 3.2e-6 ->
                             // 1.2e-6, max unchanged, kernel +7 % (LLNL) ... +16 % of the step (JetSurf): the knot-limited steps
                             // are short enough without it, so it is left off; the free-stepping dp54_kernel needs it.
 #endif
-constexpr int BS23_BLOCK = 128;
+#ifndef PFR_NORM_NEW_ONLY
+#define PFR_NORM_NEW_ONLY 1   // bs23: error weights atol + rtol |y1| instead of atol + rtol max(|y0|, |y1|) -- never looser, so the error control
+                              // only tightens; saves DSETP + 2 FSEL per species and step: 63.7 -> 62.7 ms at 2^20 conditions (r02m / r02n A/B)
+#endif
+constexpr int BS23_BLOCK = PFR_BS23_BLOCK;
 #ifndef PFR_BS23_MINB
 #define PFR_BS23_MINB (PFR_BS23_SMEM_STATE ? 3 : 2)   // CTAs per SM: 168 registers / 12 warps with the shared-memory state, else 252 / 8
 #endif
@@ -134,6 +142,25 @@ __device__ __forceinline__ int bound_key(double b) { return __double2hiint(fabs(
 __device__ __forceinline__ int bound_key(float b) { return __float_as_int(fabsf(b)); }
 __device__ __forceinline__ bool maybe_outside(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) >= thr; }
 __device__ __forceinline__ bool maybe_outside(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) >= thr; }
+// the same test over a whole 9-vector: "some |x_j| >= bound (or NaN)".  Positive entries are caught by the SIGNED maximum of the high
+// words (negative doubles are negative integers there), negative ones by the UNSIGNED maximum (their sign bit makes them the largest
+// unsigned values, ordered by magnitude): two 3-input integer max chains (VIMNMX3) and two compares -- 10 instructions instead of
+// the 18 of nine masked compares.
+__device__ __forceinline__ int key_word(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int key_word(float x) { return __float_as_int(x); }
+template <typename real, int N>
+__device__ __forceinline__ bool any_outside(const real (&x)[N], int thr) {
+    static_assert(N % 2 == 1, "pairs after the first entry");
+    int ms = key_word(x[0]);
+    unsigned mu = (unsigned)ms;
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+        const int a = key_word(x[j]), b = key_word(x[j + 1]);
+        ms = max(ms, max(a, b));
+        mu = max(mu, max((unsigned)a, (unsigned)b));
+    }
+    return ms >= thr || mu >= ((unsigned)thr | 0x80000000u);
+}
 
 // Temperature part of the exponents: kT_j = lnA_j - Ea_j / (R T) + b_j ln T
 template <typename real>
@@ -160,20 +187,15 @@ __device__ __forceinline__ void arrhenius_uni(const CrnnParams<real>& p, const T
     for (int j = 0; j < NR; j++) kT[j] = fma(cd.arr[copy][j][0], mE, fma(cd.arr[copy][j][1], lnT, cd.arr[copy][j][2]));
 }
 
-// du = f(y) at given kT: streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
-// min(|zlo|, |zhi|) and min(|dulo|, |duhi|): the exponent and output clamps are skipped when no entry comes near them.
-template <typename real, int kUniRows>
-__device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, int zthr, int dthr,
-                                           const real (&kT)[NR], const real (&y)[NS], real (&du)[NS]) {
-    // (kT, nu and therefore z are in units of ln2 / 256 -- z_scale; zthr is the key of the scaled clamp bound)
-    real z[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++) z[j] = kT[j];
+// z_j += sum_k nu[k][j] ln clamp(y_k): the first mat-vec of the right-hand side, streaming over the species (kUpper: with the upper
+// state clamp; see rhs_tpc_kT)
+template <typename real, int kUniRows, bool kUpper>
+__device__ __forceinline__ void exponents_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy,
+                                              const real (&y)[NS], real (&z)[NR]) {
 #pragma unroll
     for (int k = 0; k < NS; k++) {
-        // (deciding the state clamp on the integer pipe -- high-word test, exact clamp only when some species is not strictly
-        // inside -- was measured 6 % SLOWER than these 2 DSETP + 4 FSEL per species: the rare branch costs more than it saves)
-        const real l = t_log<real>(m_min(m_max(y[k], p.lb), p.ub), sc.ft);
+        const real yc = m_max(y[k], p.lb);
+        const real l = t_log<real>(kUpper ? m_min(yc, p.ub) : yc, sc.ft);
         if ((kUniRows >> k) & 1) {
 #pragma unroll
             for (int j = 0; j < NR; j++) z[j] = fma(cd.nu[copy][k][j], l, z[j]);
@@ -184,10 +206,24 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
             for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
         }
     }
-    bool near = false;
+}
+
+// du = f(y) at given kT: streaming form, 18 live values (the exponents z_j, then the sums du_i).  zthr / dthr: bound_key of
+// min(|zlo|, |zhi|) and min(|dulo|, |duhi|): the exponent and output clamps are skipped when no entry comes near them.
+template <typename real, int kUniRows>
+__device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy, int zthr, int dthr,
+                                           const real (&kT)[NR], const real (&y)[NS], real (&du)[NS]) {
+    // (kT, nu and therefore z are in units of ln2 / 256 -- z_scale; zthr is the key of the scaled clamp bound)
+    real z[NR];
 #pragma unroll
-    for (int j = 0; j < NR; j++) near = near || maybe_outside(z[j], zthr);
-    if (near) {
+    for (int j = 0; j < NR; j++) z[j] = kT[j];
+    // (The state clamp stays 2 DSETP + 4 FSEL per species.  Measured alternatives, both SLOWER: deciding it on the integer pipe with the
+    // exact clamp in a branch taken when some species is not strictly inside, -6 %; handling only the upper bound that way -- a signed
+    // maximum over the high words, REDUX over the warp so that the branch is uniform, a second copy of this loop with the two-sided
+    // clamp behind it -- 64.0 -> 69.4 ms: the branch keeps the scheduler from overlapping the first logarithms with the tail of the
+    // previous stage.)
+    exponents_tpc<real, kUniRows, true>(p, sc, cd, copy, y, z);
+    if (any_outside(z, zthr)) {
 #pragma unroll
         for (int j = 0; j < NR; j++) z[j] = m_min(m_max(z[j], z_scale<real>() * p.zlo), z_scale<real>() * p.zhi);
     }
@@ -206,10 +242,7 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
             for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
         }
     }
-    near = false;
-#pragma unroll
-    for (int i = 0; i < NS; i++) near = near || maybe_outside(du[i], dthr);
-    if (near) {
+    if (any_outside(du, dthr)) {
 #pragma unroll
         for (int i = 0; i < NS; i++) du[i] = m_min(m_max(du[i], p.dulo), p.duhi);
     }
@@ -384,13 +417,17 @@ bs23_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
           if (active) {
             nrhs += 3;
             real e2 = real(0);
-            bool finite = true;
+            // |w_k| < 1e30 and not NaN for every species, on the integer pipe (any_outside: two 3-input max chains over the high words)
+            bool finite = !any_outside(w, bound_key(real(1e30)));
 #pragma unroll
             for (int k = 0; k < NS; k++) {
                 const real ek = h * fma(real(-1.0 / 8.0), k2[k], ER(k));
+#if PFR_NORM_NEW_ONLY
+                const real isk = rcp_norm(atol + rtol * m_abs(w[k]));
+#else
                 const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
+#endif
                 e2 = fma(ek * isk, ek * isk, e2);
-                finite = finite && (m_abs(w[k]) < real(1e30));
             }
             real err = m_sqrt<real>(e2 / real(NS));
 #if PFR_BS23_KINK
@@ -605,7 +642,7 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
             nrhs += fresh ? 1 : DP54_STAGES - 1;
             // w = y1 (row 6 of the tableau = the 5th-order weights), f = f(y1)   [entry step: w = y0, f = f(y0), h = 0]
             real e2 = real(0);
-            bool finite = true;
+            bool finite = !any_outside(w, bound_key(real(1e30)));   // (as in bs23_kernel)
 #pragma unroll
             for (int k = 0; k < NS; k++) {
                 real ek = real(0);
@@ -614,7 +651,6 @@ dp54_kernel(const __grid_constant__ CrnnParams<real> p, const __grid_constant__ 
                 ek *= h;
                 const real isk = rcp_norm(atol + rtol * m_max(m_abs(y[k]), m_abs(w[k])));
                 e2 = fma(ek * isk, ek * isk, e2);
-                finite = finite && (m_abs(w[k]) < real(1e30));
             }
             real err = m_sqrt<real>(e2 / real(NS));
             // A step during which a species crosses the lower state clamp straddles a kink of the right-hand side

@@ -34,7 +34,7 @@ TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eo
 # sit at 1e-6 ... 1e-3 mol/m3 are governed by atol, everything else by rtol, so the two are set separately.
 FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "taylor4": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-7)}
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
-           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP,
+           "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP, "dp54w": _lib.METHOD_DP54_WARP,
            "taylor4": _lib.METHOD_TAYLOR4}
 
 
@@ -309,7 +309,7 @@ class Surrogate:
                                             _ptr(Tprof), _ptr(t_end), _ptr(idx_end), _ptr(perm), rtol, atol, max_steps, int(bool(dense_raw)), _ptr(y),
                                             _ptr(yd), _ptr(status), _ptr(stats), _stream()), "pfr_integrate")
         res = SolveResult(y, status, stats, yd, t_end, idx_end, tgrid, Tprof)
-        if method in ("bs23", "bs23w", "taylor4", "dp54") and stiff_fallback:
+        if method in ("bs23", "bs23w", "taylor4", "dp54", "dp54w") and stiff_fallback:
             # The explicit fast paths stop a condition whose steps turn out stability-limited with PFR_ST_STIFF; those conditions
             # (none for the shipped parameter sets) are integrated again, from the inlet, with the Rosenbrock kernel and their
             # results written over the flagged entries.  List and count stay on the device (pfr_stiff_fallback): no host sync.

@@ -161,11 +161,22 @@ def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     return packed
 
 
+# (rtol, atol) of the free-stepping forward pass of the isothermal trainers ("dp54w"): knot states within ~1e-7 of the converged
+# trajectory, i.e. at least as close as the knot-limited pass they replace at the reference's 1e-4 / 1e-6
+FREE_STEP_TOLERANCE = (1.0e-7, 1.0e-10)
+
+
 class CrnnTrainer:
-    """loss / gradient / optimiser step for the flat parameter vector p[189]."""
+    """loss / gradient / optimiser step for the flat parameter vector p[189].
+
+    substeps: RK4 sub-steps of the adjoint sweep per knot interval.  One is the default: against float64 central differences of
+    the oracle loss the gradient is then within 5.6e-6 of its scale (two: 1.2e-6, four: 1.2e-6 -- the finite differences' own
+    floor; tests/test_training.py), and with parameters 5 % off their trained values within 2.7e-4 of the four-sub-step gradient
+    (two: 8.6e-5; tools/adjoint_substeps.py, profiles/r02q_adjoint_substeps.jsonl) -- two orders below the solver-tolerance
+    noise of the reference's own back-propagated gradient -- for 1.9 instead of 3.5 ms per 640 conditions."""
 
     def __init__(self, batch: TrainingBatch, spec: ConverterSpec = WIDE_LLNL, clamps=TRAINING_WIDE_CLAMPS, rtol=1e-4, atol=1e-6,
-                 substeps=2, lr=5e-4, weight_decay=1e-4, clip=10.0, group=None, settings: "TrainerSettings | None" = None):
+                 substeps=1, lr=5e-4, weight_decay=1e-4, clip=10.0, group=None, settings: "TrainerSettings | None" = None):
         if settings is not None:
             clamps, rtol, atol, lr, weight_decay, clip = (settings.clamps, settings.rtol, settings.atol, settings.lr,
                                                           settings.weight_decay, settings.clip)
@@ -184,7 +195,12 @@ class CrnnTrainer:
         # which the explicit fast path is 2-4x cheaper than the Rosenbrock kernel (stiff conditions fall back to it)
         # ("bs23w": that integrator with one condition per warp -- a training batch is a few hundred conditions, so the pass is
         # latency-bound and nine lanes per right-hand side make it ~4x shorter than one thread per condition, "bs23")
-        self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "bs23w")
+        # Isothermal batches (the wide / narrow Eoff trainers): "dp54w" -- nothing ties a step to a knot at constant temperature, so
+        # the pass takes free Dormand-Prince steps (a few dozen instead of 800) and reads the 801 knot states off the method's
+        # continuous extension, as torchdiffeq's dopri5 does for the reference (WIDE_Eoff_surrogate_model_training.py:383).  A
+        # free step's error sits AT the tolerance (a knot-limited one far below it), so the pass runs at FREE_STEP_TOLERANCE or the
+        # trainer's own tolerances, whichever is tighter.
+        self.forward_method = os.environ.get("PFR_TRAIN_FORWARD", "dp54w" if batch.Tprof is None else "bs23w")
         self._crnn, self._bufs, self.failed_last = None, {}, 0
         # gradient kernels: "staged" = three kernels with a workspace of 3.8 MB per condition (pfr_loss_grad_staged), "warp" = the
         # single kernel, one condition per warp, no workspace (pfr_loss_grad); "auto" = staged while the workspace stays under 8 GB
@@ -207,8 +223,12 @@ class CrnnTrainer:
         """Raw knot states [801, 9, n] (float64) of the current parameters; status [n]."""
         crnn = self._model(w_in, w_b, w_out)
         b = batch or self.batch
-        res = self._sur.integrate(b.T0, b.c0, tgrid=b.tgrid, Tprof=b.Tprof, rtol=self.rtol, atol=self.atol, dense=True, dense_raw=True,
-                                  method=self.forward_method)
+        method = self.forward_method if b.Tprof is None or self.forward_method != "dp54w" else "bs23w"
+        rtol, atol = self.rtol, self.atol
+        if method == "dp54w":
+            rtol, atol = min(rtol, FREE_STEP_TOLERANCE[0]), min(atol, FREE_STEP_TOLERANCE[1])
+        res = self._sur.integrate(b.T0, b.c0, tgrid=b.tgrid, Tprof=b.Tprof, rtol=rtol, atol=atol, dense=True, dense_raw=True,
+                                  method=method)
         return crnn, res
 
     def _buffers(self, n: int):

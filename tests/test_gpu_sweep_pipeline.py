@@ -118,3 +118,55 @@ def test_warp_per_condition_bs23_equals_thread_per_condition(surrogates, golden,
         sub = s.integrate(T[:m], c0[:m], method="bs23w", tgrid=ref.tgrid[:, :m].contiguous(), Tprof=None if ref.Tprof is None else ref.Tprof[:, :m].contiguous(),
                           idx_end=idx[:m].contiguous(), rtol=1e-8, atol=1e-10)
         assert torch.equal(sub.y, b.y[:, :m])
+
+
+def test_free_stepping_dp54_warp_dense_output(surrogates, golden, conditions):
+    """PFR_METHOD_DP54_WARP (the isothermal training step's forward pass): free Dormand-Prince steps over tgrid's span with the 801
+    knot states read off the method's 4th-order continuous extension.  Against the converged oracle solution (golden fixtures:
+    outlet and every 50th knot) within 1e-6 at rtol 1e-8 / atol 1e-11; against the knot-limited BS23 pass at a tight tolerance on
+    the 400 shipped conditions within 1e-6 at EVERY knot (1e-3 mol/m3 floor) at 1e-9 / 1e-12 and within 1e-5 at the trainer's
+    setting; a few dozen steps instead of 800; outlet knots
+    short of the grid end (idx_end), degenerate ones (idx_end = 0) and ragged batch sizes handled as the other integrators do;
+    a temperature profile is refused (the method is isothermal)."""
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200 import _lib
+    from conftest import rel_err
+    s = surrogates("LLNL", "Eoff")
+    tgd = torch.as_tensor(golden["Eoff/tgrid"].T.copy()).cuda()
+    r = s.integrate(golden["T"], golden["c0"][:, 6], method="dp54w", tgrid=tgd, rtol=1e-8, atol=1e-11, dense=True, stiff_fallback=None)
+    assert int(r.status.abs().sum()) == 0
+    truth = np.clip(golden["Eoff/truth_outlet"], 1e-6, 60.0)
+    assert np.max(rel_err(r.y.cpu().numpy().T, truth)) < 1e-6
+    dense = r.dense.cpu().numpy()
+    for j, k in enumerate(range(0, 801, 50)):
+        ref = np.clip(golden["Eoff/truth_knots_every50"][:, j, :], 1e-6, 60.0)
+        assert np.max(rel_err(dense[k].T, ref)) < 1e-6, k
+    st = r.stats.cpu().numpy()
+    assert np.array_equal(st[2], 6 * (st[0] + st[1]) + 1)
+    assert (st[0] + st[1]).max() < 400
+
+    T, P, L, U = cond4(conditions)
+    ref = s.sweep(T, P, L, U, method="rodas4", keep_grids=True)      # for the grids
+    c0 = s.inlet_concentration(T, P)
+    idx = torch.full((len(T),), 800, dtype=torch.int32, device="cuda")
+    idx[::7] = 0
+    idx[1::7] = 333
+    kw = dict(tgrid=ref.tgrid, idx_end=idx, dense=True, dense_raw=True)
+    from n_hexane_pyrolysis_surrogate_reactor_model_b200.training import FREE_STEP_TOLERANCE
+    a = s.integrate(T, c0, method="bs23", rtol=1e-10, atol=1e-13, **kw)
+    scale = a.dense.abs().clamp(min=1e-3)
+    c = s.integrate(T, c0, method="dp54w", rtol=1e-9, atol=1e-12, **kw)
+    assert int(a.status.abs().sum()) == 0 and int(c.status.abs().sum()) == 0
+    assert float(((a.dense - c.dense).abs() / scale).max()) < 1e-6
+    # at the trainer's setting (the reference trains at 1e-4 / 1e-6): every knot state within 1e-5 (measured 3.7e-6), outlets within 1e-6
+    b = s.integrate(T, c0, method="dp54w", rtol=FREE_STEP_TOLERANCE[0], atol=FREE_STEP_TOLERANCE[1], **kw)
+    assert int(b.status.abs().sum()) == 0
+    assert float(((a.dense - b.dense).abs() / scale).max()) < 1e-5
+    assert float(((a.y - b.y).abs() / a.y.abs().clamp(min=1e-3)).max()) < 1e-5
+    attempts = (b.stats[0] + b.stats[1]).float()
+    assert float(attempts[idx == 800].mean()) < 120
+    print(f"dp54w: {float(attempts[idx == 800].mean()):.0f} attempts per trajectory (bs23: {float((a.stats[0] + a.stats[1]).float()[idx == 800].mean()):.0f})")
+    for m in (1, 3, 5):
+        sub = s.integrate(T[:m], c0[:m], method="dp54w", tgrid=ref.tgrid[:, :m].contiguous(), idx_end=idx[:m].contiguous(), rtol=1e-7, atol=1e-10)
+        assert torch.equal(sub.y, b.y[:, :m])
+    with pytest.raises(_lib.PfrError):
+        s.integrate(T, c0, method="dp54w", tgrid=ref.tgrid, Tprof=ref.tgrid, rtol=1e-7, atol=1e-10)

@@ -107,6 +107,40 @@ __global__ void __launch_bounds__(128, 3) k_shared(const __grid_constant__ CoefS
     for (int i = 0; i < 9; i++) out[i * 128 + threadIdx.x + blockIdx.x * 9 * 128] = y[i];
 }
 
+// (d) fixed-address 16-byte uniform loads (LDCU.128, two coefficients per load) from a __constant__ block, issued as volatile
+//     inline PTX so that nvcc cannot hoist them out of the step loop; ptxas keeps as many as fit in uniform registers and
+//     re-loads the rest every step.  (With an index in the address -- the copy toggle of (b) -- ptxas only ever emits LDCU.64.)
+extern "C" { __constant__ CoefS pfr_cc; }
+template <int OFF>
+__device__ __forceinline__ void ldc2(double& a, double& b) {
+    asm volatile("ld.const.v2.f64 {%0, %1}, [pfr_cc+%2];" : "=d"(a), "=d"(b) : "n"(OFF));
+}
+template <int BASE, int KK, int J>
+struct RowC {
+    static __device__ __forceinline__ void run(double l, double (&z)[10]) {
+        double a, b;
+        ldc2<BASE + (KK * 10 + J) * 8>(a, b);
+        z[J] = fma(a, l, z[J]);
+        if (J + 1 < 9) z[J + 1] = fma(b, l, z[J + 1]);
+        if constexpr (J + 2 < 10) RowC<BASE, KK, J + 2>::run(l, z);
+    }
+};
+__global__ void __launch_bounds__(128, 3) k_const128(const double* __restrict__ in, double* __restrict__ out, int steps) {
+    double y[10], z[10];
+    for (int i = 0; i < 9; i++) y[i] = in[i * 128 + threadIdx.x];
+    for (int s = 0; s < steps; s++) {
+#pragma unroll
+        for (int j = 0; j < 10; j++) z[j] = 0.0;
+#define ROWN(KK) RowC<0, KK, 0>::run(y[KK] * 0.999 + 1e-3, z);
+        ROWN(0) ROWN(1) ROWN(2) ROWN(3) ROWN(4) ROWN(5) ROWN(6) ROWN(7) ROWN(8)
+#pragma unroll
+        for (int j = 0; j < 10; j++) y[j] = 0.0;
+#define ROWW(KK) RowC<720, KK, 0>::run(z[KK] * 0.5 + 0.25, y);
+        ROWW(0) ROWW(1) ROWW(2) ROWW(3) ROWW(4) ROWW(5) ROWW(6) ROWW(7) ROWW(8)
+    }
+    for (int i = 0; i < 9; i++) out[i * 128 + threadIdx.x + blockIdx.x * 9 * 128] = y[i];
+}
+
 int main() {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -122,19 +156,21 @@ int main() {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaFree(out);
     cudaMalloc(&out, (size_t)grid * 4 * 9 * 128 * sizeof(double));
-    for (int variant = 0; variant < 6; variant++) {
+    cudaMemcpyToSymbol(pfr_cc, &cs, sizeof(cs));
+    for (int variant = 0; variant < 7; variant++) {
         const int g = variant == 3 ? 2 * grid : (variant == 4 ? 4 * grid : (variant == 5 ? grid / 3 : grid));   // 6, 12 and 1 CTA(s) per SM
         for (int rep = 0; rep < 2; rep++) {
             cudaEventRecord(e0);
             if (variant == 0) k_shared<<<g, 128>>>(cs, in, out, steps);
             else if (variant == 2) k_uniform2<<<g, 128>>>(c, in, out, steps);
+            else if (variant == 6) k_const128<<<g, 128>>>(in, out, steps);
             else k_uniform<<<g, 128>>>(c, in, out, steps);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms = 0;
             cudaEventElapsedTime(&ms, e0, e1);
             const double dfma = 162.0 * 128 * g * (double)steps;
-            printf("%s: %.3f ms, %.2f TFLOP/s of DFMA, %s\n", variant == 0 ? "shared broadcast (LDS.128)" : (variant == 1 ? "uniform registers (LDCU.64)" : (variant == 2 ? "uniform registers, two accumulator sets" : (variant == 3 ? "uniform, 6 CTAs/SM" : (variant == 4 ? "uniform, 12 CTAs/SM" : "uniform, 1 CTA/SM")))), ms, 2 * dfma / (ms * 1e-3) / 1e12,
+            printf("%s: %.3f ms, %.2f TFLOP/s of DFMA, %s\n", variant == 0 ? "shared broadcast (LDS.128)" : (variant == 1 ? "uniform registers (LDCU.64)" : (variant == 2 ? "uniform registers, two accumulator sets" : (variant == 3 ? "uniform, 6 CTAs/SM" : (variant == 4 ? "uniform, 12 CTAs/SM" : (variant == 5 ? "uniform, 1 CTA/SM" : "fixed-address LDCU.128 from __constant__"))))), ms, 2 * dfma / (ms * 1e-3) / 1e12,
                    cudaGetErrorString(cudaGetLastError()));
         }
     }

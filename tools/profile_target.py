@@ -1,5 +1,5 @@
 """Small fixed workload for ncu captures: one Eon integrate, one Eoff integrate, the three MLP passes.
-Usage: python tools/profile_target.py [n] [precision] [method] [tol]"""
+Usage: python tools/profile_target.py [n] [precision] [method] [tol]   (PFR_ATOL: absolute tolerance of the Eon integrate if it differs from tol)"""
 import os
 import sys
 
@@ -22,7 +22,7 @@ def main():
     on = Surrogate(ModelSet.from_packed(gold, "Eon"))
     off = Surrogate(ModelSet.from_packed(gold, "Eoff"))
     for _ in range(2):
-        r1 = on.sweep(T, P, L, U, precision=prec, method=method, rtol=tol, atol=tol)
+        r1 = on.sweep(T, P, L, U, precision=prec, method=method, rtol=tol, atol=float(os.environ.get("PFR_ATOL", tol)))
         r2 = off.sweep(T, P, L, U, precision=prec, method=os.environ.get("PFR_EOFF_METHOD", "rodas4"), rtol=float(os.environ.get("PFR_EOFF_TOL", "1e-6")), atol=float(os.environ.get("PFR_EOFF_TOL", "1e-6")))
     torch.cuda.synchronize()
     print("ok", float(r1.y.sum()), float(r2.y.sum()), int(r1.status.sum()), int(r2.status.sum()))
