@@ -170,7 +170,7 @@ class CrnnTrainer:
     """loss / gradient / optimiser step for the flat parameter vector p[189].
 
     substeps: RK4 sub-steps of the adjoint sweep per knot interval.  One is the default: against float64 central differences of
-    the oracle loss the gradient is then within 5.6e-6 of its scale (two: 1.2e-6, four: 1.2e-6 -- the finite differences' own
+    the converged CPU loss the gradient is then within 5.6e-6 of its scale (two: 1.2e-6, four: 1.2e-6 -- the finite differences' own
     floor; tests/test_training.py), and with parameters 5 % off their trained values within 2.7e-4 of the four-sub-step gradient
     (two: 8.6e-5; tools/adjoint_substeps.py, profiles/r02q_adjoint_substeps.jsonl) -- two orders below the solver-tolerance
     noise of the reference's own back-propagated gradient -- for 1.9 instead of 3.5 ms per 640 conditions."""
