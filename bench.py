@@ -209,6 +209,8 @@ def run_ours(args, emit=print):
             ("LLNL_Eon_taylor4", "Eon", "f16x3", "taylor4", 64, bs_r, bs_a),
             ("LLNL_Eon_mlp_tf32x3", "Eon", "tf32x3", "bs23", 64, bs_r, bs_a),
             ("LLNL_Eon_mlp_fp32", "Eon", "fp32", "bs23", 64, bs_r, bs_a))
+    if args.headline_only:   # (multi-GPU scaling checks: the headline Eon sweep, the Eoff sweep and the training step only)
+        runs = runs[:2]
     sur, sur_key, grids = None, None, None
     for name, variant, mlp_mode, method, prec, rtol, atol in runs:
         if sur_key != (variant, mlp_mode):
@@ -293,8 +295,9 @@ def run_ours(args, emit=print):
     torch.cuda.empty_cache()
 
     # the other mechanisms of config 3 and the reference-behaviour integrator, device-resident timing only
-    for mech, variant, method, prec in (("JetSurf", "Eon", "bs23", 64), ("JetSurf", "Eoff", "dp54", 64), ("NUIG", "Eon", "bs23", 64),
-                                        ("NUIG", "Eoff", "dp54", 64), ("LLNL", "Eoff", "dopri5", 32), ("LLNL", "Eon", "rodas4", 32)):
+    for mech, variant, method, prec in () if args.headline_only else (
+            ("JetSurf", "Eon", "bs23", 64), ("JetSurf", "Eoff", "dp54", 64), ("NUIG", "Eon", "bs23", 64),
+            ("NUIG", "Eoff", "dp54", 64), ("LLNL", "Eoff", "dopri5", 32), ("LLNL", "Eon", "rodas4", 32)):
         sur = Surrogate(ModelSet.from_packed(os.path.join(GOLD, f"{mech}.npz"), variant), device=dev)
         rt, at = {"bs23": (bs_r, bs_a), "dp54": (dp_r, dp_a)}.get(method, (args.rtol, args.atol))
         kw2 = dict(method=method, precision=prec, rtol=rt, atol=at)
@@ -526,6 +529,7 @@ def main():
     ap.add_argument("--bs23-atol", type=float, default=1e-12, help="atol that goes with --bs23-rtol")
     ap.add_argument("--dp54-tol", type=float, default=None, help="rtol = atol of the explicit fast path on the isothermal (Eoff) path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="time the headline sweeps and the training step only (no secondary variants)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: whatever libraries print while the run is going on (NCCL's version banner, ...)
     # is sent to stderr by pointing file descriptor 1 there until the line is ready

@@ -120,6 +120,16 @@ struct DeviceCtx {
     cudaStream_t aux[AUX_STREAMS] = {};       // second lane of the MLP chunk pipeline, round robin over calls
     cudaEvent_t fork[AUX_STREAMS] = {}, join[AUX_STREAMS] = {};
     std::atomic<unsigned> next_aux{0};
+    // the device's one block of CRNN coefficients in __constant__ memory (pfr_const_coef, read by the float64 explicit integrators):
+    // what it holds, and an event behind the last launch that reads it
+    std::mutex coef_mutex;
+    ConstCoef coef_host;
+    bool coef_valid = false, coef_launched = false;
+    cudaEvent_t coef_event = nullptr;
+    static constexpr int COEF_SLOTS = 8;      // page-locked staging ring for the uploads (a pageable source would make the copy wait for the stream)
+    ConstCoef* coef_pinned = nullptr;
+    cudaEvent_t coef_slot_done[COEF_SLOTS] = {};
+    unsigned coef_slot = 0;
 };
 static DeviceCtx g_ctx[MAX_DEVICES];
 static std::mutex g_ctx_mutex;
@@ -678,6 +688,44 @@ static int next_counter(DeviceCtx& ctx, cudaStream_t st, int** out) {
     return PFR_OK;
 }
 
+// The float64 explicit integrators read their two 9 x 9 coefficient matrices from ONE __constant__ block per device (fixed
+// addresses are what lets ptxas use 16-byte uniform loads, integrate_explicit.cuh).  Launches that use the block are chained
+// through an event -- each of them fills the GPU with a persistent grid, so ordering them across streams costs nothing -- and the
+// block is re-uploaded, in stream order behind the previous launch, only when the coefficients differ from what it holds.
+static int stage_const_coef(DeviceCtx& ctx, const CrnnParams<double>& p, cudaStream_t st) {
+#if PFR_CONST_COEF
+    ConstCoef h;
+    fill_const_coef(h, p);
+    std::lock_guard<std::mutex> lock(ctx.coef_mutex);
+    if (!ctx.coef_event) {
+        CK(cudaEventCreateWithFlags(&ctx.coef_event, cudaEventDisableTiming));
+        CK(cudaMallocHost((void**)&ctx.coef_pinned, DeviceCtx::COEF_SLOTS * sizeof(ConstCoef)));
+        for (int i = 0; i < DeviceCtx::COEF_SLOTS; i++) CK(cudaEventCreateWithFlags(&ctx.coef_slot_done[i], cudaEventDisableTiming));
+    }
+    if (ctx.coef_launched) CK(cudaStreamWaitEvent(st, ctx.coef_event, 0));
+    if (!ctx.coef_valid || memcmp(&h, &ctx.coef_host, sizeof(h)) != 0) {
+        const unsigned slot = ctx.coef_slot++ % DeviceCtx::COEF_SLOTS;
+        CK(cudaEventSynchronize(ctx.coef_slot_done[slot]));   // (its previous upload, eight uploads ago: long done)
+        ctx.coef_pinned[slot] = h;
+        CK(cudaMemcpyToSymbolAsync(pfr_const_coef, &ctx.coef_pinned[slot], sizeof(h), 0, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx.coef_slot_done[slot], st));
+        ctx.coef_host = h;
+        ctx.coef_valid = true;
+    }
+#endif
+    return PFR_OK;
+}
+static int stage_const_coef(DeviceCtx&, const CrnnParams<float>&, cudaStream_t) { return PFR_OK; }
+static int const_coef_launched(DeviceCtx& ctx, const CrnnParams<double>&, cudaStream_t st) {
+#if PFR_CONST_COEF
+    std::lock_guard<std::mutex> lock(ctx.coef_mutex);
+    CK(cudaEventRecord(ctx.coef_event, st));
+    ctx.coef_launched = true;
+#endif
+    return PFR_OK;
+}
+static int const_coef_launched(DeviceCtx&, const CrnnParams<float>&, cudaStream_t) { return PFR_OK; }
+
 template <typename real>
 static int dispatch_bs23(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasArgs& a0, cudaStream_t st) {
     RodasArgs a = a0;
@@ -687,10 +735,11 @@ static int dispatch_bs23(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasA
     const int grid = full < persistent ? full : persistent;
     CoefDup<real> cd;
     fill_coef_dup(cd, p);
+    if ((rc = stage_const_coef(ctx, p, st))) return rc;
     if (a.Tprof) bs23_kernel<real, true><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, cd, a);
     else bs23_kernel<real, false><<<grid, BS23_BLOCK, bs23_smem_bytes<real>(), st>>>(p, cd, a);
     CK_LAUNCH("bs23_kernel");
-    return PFR_OK;
+    return const_coef_launched(ctx, p, st);
 }
 
 template <typename real>
@@ -714,9 +763,10 @@ static int dispatch_dp54(DeviceCtx& ctx, const CrnnParams<real>& p, const RodasA
     const int full = (a.n + DP54_BLOCK - 1) / DP54_BLOCK, persistent = DP54_CTAS_PER_SM * ctx.num_sms;
     CoefDup<real> cd;
     fill_coef_dup(cd, p);
+    if ((rc = stage_const_coef(ctx, p, st))) return rc;
     dp54_kernel<real><<<full < persistent ? full : persistent, DP54_BLOCK, dp54_smem_bytes<real>(), st>>>(p, cd, a);
     CK_LAUNCH("dp54_kernel");
-    return PFR_OK;
+    return const_coef_launched(ctx, p, st);
 }
 
 template <typename real>

@@ -122,6 +122,46 @@ static inline void fill_coef_dup(CoefDup<real>& d, const CrnnParams<real>& p) {
         }
 }
 
+// Third feed, an experiment that is OFF by default (PFR_CONST_COEF=1 builds it): the same block in __constant__ memory at FIXED
+// addresses, read two coefficients per uniform 16-byte load (LDCU.128).  ptxas only ever emits LDCU.64 when the address carries an
+// index (the copy toggle above), so this path uses immediate offsets, and the loads are volatile inline PTX so that nvcc cannot
+// hoist 162 loop-invariant values out of the step loop.  In isolation it is the fastest feed (tools/micro/coef_paths.cu,
+// profiles/r02o_coef_feed_microbench.txt: a 9x9 mat-vec pair at 21.4 TFLOP/s against 18.3 with LDCU.64 and 16.6 with broadcast
+// LDS.128).  In the kernels it is not: ptxas parks the first ~23 coefficients in uniform registers for the whole loop (they ARE
+// loop-invariant) and streams all the others through the four registers that are left -- every LDCU.128 waits for the two
+// DFMAs that read its predecessor, the load latency is exposed 70 times per right-hand side: bs23_kernel 62.0 -> 76.9 ms,
+// dp54_kernel 6.5 -> 6.25 ms at 2^20 conditions (profiles/r02s_const_coef_ab.jsonl), results bit-identical.  The block is one
+// per device: the host side (stage_const_coef in capi.cu) re-uploads it in stream order when the model changes and chains the
+// launches that read it.
+#ifndef PFR_CONST_COEF
+#define PFR_CONST_COEF 0
+#endif
+struct __align__(16) ConstCoef {
+    double nu[NS][10];      // [k][j], in units of ln2 / 256 (z_scale), j = 9: 0
+    double woutT[NR][10];   // [j][i], i = 9: 0
+};
+extern "C" { __constant__ ConstCoef pfr_const_coef; }
+static inline void fill_const_coef(ConstCoef& d, const CrnnParams<double>& p) {
+    for (int r = 0; r < NS; r++)
+        for (int e = 0; e < 10; e++) {
+            d.nu[r][e] = e < NR ? z_scale<double>() * p.nu[r][e] : 0.0;
+            d.woutT[r][e] = e < NS ? p.wout[e][r] : 0.0;
+        }
+}
+template <int kOffset>
+__device__ __forceinline__ void ldc2(double& a, double& b) {
+    asm volatile("ld.const.v2.f64 {%0, %1}, [pfr_const_coef+%2];" : "=d"(a), "=d"(b) : "n"(kOffset));
+}
+// acc[j] += C[kRow][j] * x, j = 0..8, for the matrix that starts kBase bytes into the block
+template <int kBase, int kRow, int kJ = 0>
+__device__ __forceinline__ void row_fma_const(double x, double (&acc)[9]) {
+    double a, b;
+    ldc2<kBase + (kRow * 10 + kJ) * 8>(a, b);
+    acc[kJ] = fma(a, x, acc[kJ]);
+    if constexpr (kJ + 1 < 9) acc[kJ + 1] = fma(b, x, acc[kJ + 1]);
+    if constexpr (kJ + 2 < 9) row_fma_const<kBase, kRow, kJ + 2>(x, acc);
+}
+
 // volatile: the values are loop-invariant; a plain load lets the compiler hoist all of them out of the step loop.  `after`
 // is an artificial input: the load may not be scheduled before that value exists, which keeps the nine coefficient rows
 // of a mat-vec from being fetched (and held in 180 registers) ahead of the logarithms / exponentials they multiply.
@@ -189,21 +229,37 @@ __device__ __forceinline__ void arrhenius_uni(const CrnnParams<real>& p, const T
 
 // z_j += sum_k nu[k][j] ln clamp(y_k): the first mat-vec of the right-hand side, streaming over the species (kUpper: with the upper
 // state clamp; see rhs_tpc_kT)
+template <bool kUpper, int kK = 0>
+__device__ __forceinline__ void exponents_const(const CrnnParams<double>& p, const FastTables& ft, const double (&y)[NS], double (&z)[NR]) {
+    const double yc = m_max(y[kK], p.lb);
+    row_fma_const<0, kK>(fast_log(kUpper ? m_min(yc, p.ub) : yc, ft.logtab), z);
+    if constexpr (kK + 1 < NS) exponents_const<kUpper, kK + 1>(p, ft, y, z);
+}
+template <int kJ = 0>
+__device__ __forceinline__ void rates_const(const FastTables& ft, const double (&z)[NR], double (&du)[NS]) {
+    row_fma_const<(int)sizeof(double) * NS * 10, kJ>(fast_exp_scaled(z[kJ], ft.exptab), du);
+    if constexpr (kJ + 1 < NR) rates_const<kJ + 1>(ft, z, du);
+}
+
 template <typename real, int kUniRows, bool kUpper>
 __device__ __forceinline__ void exponents_tpc(const CrnnParams<real>& p, const TpcCoef<real>& sc, const CoefDup<real>& cd, int copy,
                                               const real (&y)[NS], real (&z)[NR]) {
+    if constexpr (sizeof(real) == 8 && PFR_CONST_COEF) {
+        exponents_const<kUpper>(p, sc.ft, y, z);
+    } else {
 #pragma unroll
-    for (int k = 0; k < NS; k++) {
-        const real yc = m_max(y[k], p.lb);
-        const real l = t_log<real>(kUpper ? m_min(yc, p.ub) : yc, sc.ft);
-        if ((kUniRows >> k) & 1) {
+        for (int k = 0; k < NS; k++) {
+            const real yc = m_max(y[k], p.lb);
+            const real l = t_log<real>(kUpper ? m_min(yc, p.ub) : yc, sc.ft);
+            if ((kUniRows >> k) & 1) {
 #pragma unroll
-            for (int j = 0; j < NR; j++) z[j] = fma(cd.nu[copy][k][j], l, z[j]);
-        } else {
-            real c[10];
-            lds9(sc.nu[k], c, l);
+                for (int j = 0; j < NR; j++) z[j] = fma(cd.nu[copy][k][j], l, z[j]);
+            } else {
+                real c[10];
+                lds9(sc.nu[k], c, l);
 #pragma unroll
-            for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
+                for (int j = 0; j < NR; j++) z[j] = fma(c[j], l, z[j]);
+            }
         }
     }
 }
@@ -229,17 +285,21 @@ __device__ __forceinline__ void rhs_tpc_kT(const CrnnParams<real>& p, const TpcC
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) du[i] = real(0);
+    if constexpr (sizeof(real) == 8 && PFR_CONST_COEF) {
+        rates_const(sc.ft, z, du);
+    } else {
 #pragma unroll
-    for (int j = 0; j < NR; j++) {
-        const real r = t_exp_scaled<real>(z[j], sc.ft);
-        if ((kUniRows >> j) & 1) {
+        for (int j = 0; j < NR; j++) {
+            const real r = t_exp_scaled<real>(z[j], sc.ft);
+            if ((kUniRows >> j) & 1) {
 #pragma unroll
-            for (int i = 0; i < NS; i++) du[i] = fma(cd.woutT[copy][j][i], r, du[i]);
-        } else {
-            real c[10];
-            lds9(sc.woutT[j], c, r);
+                for (int i = 0; i < NS; i++) du[i] = fma(cd.woutT[copy][j][i], r, du[i]);
+            } else {
+                real c[10];
+                lds9(sc.woutT[j], c, r);
 #pragma unroll
-            for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
+                for (int i = 0; i < NS; i++) du[i] = fma(c[i], r, du[i]);
+            }
         }
     }
     if (any_outside(du, dthr)) {
