@@ -353,8 +353,9 @@ def run_ours(args, emit=print):
                      "kernel_share_of_step": e["integrator_share_of_step"],
                      "traffic": traffic_model, "traffic_per_condition": traffic_model / n,
                      "traffic_source": "derived in this run from the outlet knots walked (inputs 12 B, 8 B per knot up to idx_cut + 2, results 88 B); "
-                                       "ncu on the same kernel: 4.21 KB per condition, L2 hit rate 71 % (profiles/r02b_ncu_full_bs23_dp54_fp64.txt; "
-                                       "round 1, reads gathered through a permutation: 74.8 KB)",
+                                       "ncu on the same kernel: 4.2 KB per condition at 2^17 conditions (L2 hit rate 71 %, "
+                                       "profiles/r02b_ncu_full_bs23_dp54_fp64.txt), 10.8 KB at 2^19 (57 %, profiles/r02p_ncu_full_bs23_fp64.txt); "
+                                       "round 1, reads gathered through a permutation: 74.8 KB",
                      "flop_model": f"2 flop per FP64-pipe instruction of the algorithm as shipped: RHS {FP64_RHS_EXPL} (+{FP64_RHS_T_EXPL} on a T ramp; "
                                    f"two 9x9 mat-vecs, 9 log + 9 exp at 8 instructions each, 18 clamp compares), BS23 step overhead {FP64_STEP_BS23} "
                                    f"(stage sums, error norm); the Rosenbrock variants: RHS {FP64_RHS} (+{FP64_RHS_T}), step ROS3 {FP64_STEP_ROS3}, "
