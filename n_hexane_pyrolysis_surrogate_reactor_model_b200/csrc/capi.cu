@@ -498,7 +498,10 @@ static int mlp_run_tc_chunks(DeviceCtx& ctx, pfr_mlp_t m, const float* T, const 
         const int rows = round_up(mv, tc::BM);
         const bool half = m->mode == PFR_MLP_F16X3;
         auto layer1 = half ? tc::mlp_tc_layer1_kernel<true> : tc::mlp_tc_layer1_kernel<false>;
-        layer1<<<(unsigned)((rows + 63) / 64), 256, 0, ls>>>(   // 8 warps per block, 8 rows per warp
+        // 8 warps per block; at most two blocks per SM, each warp walking rows with a grid stride: a warp reads its lanes' 80
+        // weights / biases into registers once and amortises that over >= 32 rows of a full chunk
+        const unsigned l1_blocks = (unsigned)((rows + 63) / 64), l1_cap = 2u * (unsigned)ctx.num_sms;
+        layer1<<<l1_blocks < l1_cap ? l1_blocks : l1_cap, 256, 0, ls>>>(
             m->W1, m->b1, m->in_dim, m->sc.lo[0], m->sc.lo[1], m->sc.lo[2], m->sc.lo[3], m->sc.span[0], m->sc.span[1],
             m->sc.span[2], m->sc.span[3], m->sc.fullL, m->sc.fullU, T + c0, P + c0, L ? L + c0 : nullptr, U ? U + c0 : nullptr, mv,
             rows, Ahi[l], Alo[l]);

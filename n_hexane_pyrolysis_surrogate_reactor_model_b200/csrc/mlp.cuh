@@ -158,14 +158,23 @@ enforce_strict_kernel(float* __restrict__ g, size_t ld, int m, float* __restrict
     if (i >= m) return;
     float prev = 0.f;
     if (row0) row0[i] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < MLP_OUT; k++) {
-        float v = g[(size_t)k * ld + i];
-        if (v <= prev) {
-            v = __fadd_rn(prev, 1e-5f);
-            if (write_back) g[(size_t)k * ld + i] = v;
+    // The scan is sequential in k, the loads are not: a batch of ES_BATCH rows is fetched into registers before it is scanned, so
+    // that a thread has ES_BATCH loads in flight instead of one (the conditional store to the same array keeps the compiler from
+    // hoisting the loads of a plain unrolled loop above it).  231 -> 9x us per 75 776-condition lane.
+    constexpr int ES_BATCH = 16;
+    static_assert(MLP_OUT % ES_BATCH == 0, "whole batches");
+    for (int k0 = 0; k0 < MLP_OUT; k0 += ES_BATCH) {
+        float v[ES_BATCH];
+#pragma unroll
+        for (int e = 0; e < ES_BATCH; e++) v[e] = g[(size_t)(k0 + e) * ld + i];
+#pragma unroll
+        for (int e = 0; e < ES_BATCH; e++) {
+            if (v[e] <= prev) {
+                v[e] = __fadd_rn(prev, 1e-5f);
+                if (write_back) g[(size_t)(k0 + e) * ld + i] = v[e];
+            }
+            prev = v[e];
         }
-        prev = v;
     }
     if (t_end) t_end[i] = prev;
 }

@@ -453,20 +453,30 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
 // layer 1 (K <= 4) fused with the input scaling, written K-major as a hi/lo pair (TF32 pairs in float32 containers, or
 // float16 pairs).  One warp per condition row: the four scaled inputs (IEEE divisions, as the reference computes them) once
 // per lane, then lane l produces 16 outputs in runs of 16 bytes per array so that every store instruction of the warp writes
-// 512 contiguous bytes.  Memory-bound on the 4 KB (2 KB) it writes per condition.
+// 512 contiguous bytes.  Memory-bound on the 4 KB (2 KB) it writes per condition; a warp walks rows with a grid stride.
 template <bool kHalf>
 __global__ void __launch_bounds__(256)
 mlp_tc_layer1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, float lo0, float lo1, float lo2,
                      float lo3, float sp0, float sp1, float sp2, float sp3, float fullL, float fullU,
                      const float* __restrict__ T, const float* __restrict__ P, const float* __restrict__ L,
                      const float* __restrict__ U, int m_valid, int rows, float* __restrict__ Hhi, float* __restrict__ Hlo) {
-    __shared__ float w_s[4 * KDIM], b_s[KDIM];     // w_s[i][k]: input-major copy of fc1.weight ([512][in_dim])
-    for (int e = threadIdx.x; e < KDIM; e += blockDim.x) {
-        b_s[e] = b1[e];
-        for (int i = 0; i < 4; i++) w_s[i * KDIM + e] = i < in_dim ? W1[e * in_dim + i] : 0.f;
-    }
-    __syncthreads();
+    // Lane l always produces the same 16 outputs (outputs k0 .. k0 + RUN - 1 of each 32 RUN wide slab), so their fc1 rows and biases live in REGISTERS
+    // for the whole kernel (a shared-memory copy indexed by k0 = RUN * lane put the 32 lanes on 4 banks: an 8-way conflict on every
+    // weight read, 134 us per 75 776-condition lane for a kernel that only has 155 MB to write).  Missing inputs (in_dim = 2) carry
+    // zero weights: fma(x, 0, acc) == acc, so the sum is the one of the FP32 path, i ascending.
+    constexpr int RUN = kHalf ? 8 : 4;           // outputs per 16-byte store
+    constexpr int NJ = KDIM / (32 * RUN);
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float w_r[NJ][RUN][4], b_r[NJ][RUN];
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+#pragma unroll
+        for (int t = 0; t < RUN; t++) {
+            const int k = 32 * RUN * j + RUN * lane + t;
+            b_r[j][t] = b1[k];
+#pragma unroll
+            for (int i = 0; i < 4; i++) w_r[j][t][i] = i < in_dim ? W1[k * in_dim + i] : 0.f;
+        }
     for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < rows; m += gridDim.x * wpb) {
         const int ms = m < m_valid ? m : m_valid - 1;
         float x[4];
@@ -474,16 +484,16 @@ mlp_tc_layer1_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
         x[1] = __fdiv_rn(__fsub_rn(P[ms], lo1), sp1);
         x[2] = in_dim > 2 ? __fdiv_rn(__fsub_rn(L ? L[ms] : fullL, lo2), sp2) : 0.f;
         x[3] = in_dim > 2 ? __fdiv_rn(__fsub_rn(U ? U[ms] : fullU, lo3), sp3) : 0.f;
-        constexpr int RUN = kHalf ? 8 : 4;           // outputs per 16-byte store
 #pragma unroll
-        for (int j = 0; j < KDIM / (32 * RUN); j++) {
+        for (int j = 0; j < NJ; j++) {
             const int k0 = 32 * RUN * j + RUN * lane;
             float a[RUN];
 #pragma unroll
             for (int t = 0; t < RUN; t++) {
                 float acc = 0.f;
-                for (int i = 0; i < in_dim; i++) acc = fmaf(x[i], w_s[i * KDIM + k0 + t], acc);   // i ascending, like the FP32 path
-                a[t] = fmaxf(acc + b_s[k0 + t], 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc = fmaf(x[i], w_r[j][t][i], acc);   // i ascending, like the FP32 path
+                a[t] = fmaxf(acc + b_r[j][t], 0.f);
             }
             if constexpr (kHalf) {
                 uint32_t hp[4], lp[4];
