@@ -202,6 +202,7 @@ def run_ours(args, emit=print):
             ("LLNL_Eon_bs23_loose", "Eon", "f16x3", "bs23", 64, 1e-6, 1e-12),
             ("LLNL_Eon_bs23_round1_setting", "Eon", "f16x3", "bs23", 64, 1e-8, 1e-8),
             ("LLNL_Eon_fast32", "Eon", "f16x3", "bs23", 32, 1e-7, 1e-7),
+            ("LLNL_Eoff_loose", "Eoff", "f16x3", "dp54", 64, 1e-7, 1e-7),
             ("LLNL_Eoff_fast32", "Eoff", "f16x3", "dp54", 32, 1e-7, 1e-7),
             ("LLNL_Eoff_rodas4", "Eoff", "f16x3", "rodas4", 64, args.rtol, args.atol),
             ("LLNL_Eon_ros3", "Eon", "f16x3", "ros3", 64, args.ros3_tol, args.ros3_tol),
@@ -288,7 +289,8 @@ def run_ours(args, emit=print):
                 accuracy = {"reference_solution": "RODAS4 at rtol = atol = 1e-11 on the same grids", "conditions": entry["accuracy"]["conditions"],
                             "error": "max over species of |y - y_ref| / max(|y_ref|, 1e-3 mol/m3) at the outlet",
                             "parity_bound": 1e-6, "headline": entry["accuracy"]}
-    for nm in ("LLNL_Eon_bs23_loose", "LLNL_Eon_bs23_round1_setting", "LLNL_Eon_fast32", "LLNL_Eon_taylor4", "LLNL_Eon_ros3", "LLNL_Eon_rodas4"):
+    for nm in ("LLNL_Eon_bs23_loose", "LLNL_Eon_bs23_round1_setting", "LLNL_Eon_fast32", "LLNL_Eon_taylor4", "LLNL_Eon_ros3", "LLNL_Eon_rodas4",
+               "LLNL_Eoff", "LLNL_Eoff_loose", "LLNL_Eoff_fast32", "LLNL_Eoff_rodas4"):
         if accuracy is not None and "accuracy" in variants.get(nm, {}):
             accuracy[nm] = dict(variants[nm]["accuracy"], rtol=variants[nm]["rtol"], atol=variants[nm]["atol"])
     del sur, grids
@@ -528,7 +530,7 @@ def main():
     ap.add_argument("--ros3-tol", type=float, default=1e-7, help="rtol = atol of the 3-stage Rosenbrock method on the Eon path")
     ap.add_argument("--bs23-rtol", type=float, default=None, help="rtol of the explicit fast path on the Eon path (default: FAST_TOLERANCE)")
     ap.add_argument("--bs23-atol", type=float, default=1e-12, help="atol that goes with --bs23-rtol")
-    ap.add_argument("--dp54-tol", type=float, default=None, help="rtol = atol of the explicit fast path on the isothermal (Eoff) path")
+    ap.add_argument("--dp54-tol", type=float, default=None, help="rtol = atol of the explicit fast path on the isothermal (Eoff) path (default: FAST_TOLERANCE, rtol 1e-7 / atol 1e-10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="time the headline sweeps and the training step only (no secondary variants)")
     args = ap.parse_args()

@@ -32,7 +32,10 @@ TRAINING_NARROW_CLAMPS = (1.0e-5, 6.0e1, -3.0e1, 3.0e1, -1.0e5, 1.0e5)  # Eon/Eo
 # (rtol, atol) at which bench.py runs the explicit fast paths.  Coupled path (bs23): the loosest pair measured to keep EVERY one of
 # 65 536 sampled LHS conditions within 1e-6 of the tight-tolerance solution (max 5.8e-7): the trace species that
 # sit at 1e-6 ... 1e-3 mol/m3 are governed by atol, everything else by rtol, so the two are set separately.
-FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "taylor4": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-7)}
+# Isothermal path (dp54), same finding: at rtol = atol = 1e-7 a third of the sampled conditions sit outside 1e-6 (max 9.5e-6, all
+# atol-governed trace species); rtol 1e-7 with atol 1e-10 brings every sampled LLNL / JetSurf condition inside (max 3.9e-7 / 4.9e-7)
+# for 1.5 ms more per 2^20 conditions (profiles/r02v_tolsplit_eoff.jsonl; NUIG Eoff needs rtol 1e-8 as well).
+FAST_TOLERANCE = {"bs23": (3.0e-7, 1.0e-12), "taylor4": (3.0e-7, 1.0e-12), "dp54": (1.0e-7, 1.0e-10)}
 METHODS = {"rodas4": _lib.METHOD_RODAS4, "dopri5": _lib.METHOD_DOPRI5, "rodas4_tpc": _lib.METHOD_RODAS4_TPC,
            "ros3": _lib.METHOD_ROS3, "bs23": _lib.METHOD_BS23, "dp54": _lib.METHOD_DP54, "bs23w": _lib.METHOD_BS23_WARP, "dp54w": _lib.METHOD_DP54_WARP,
            "taylor4": _lib.METHOD_TAYLOR4}
