@@ -32,7 +32,7 @@ constexpr double EXP_ARG_SCALE = 369.329930467574632284;   // 256 / ln 2: fast_e
 constexpr double LOG_L2 = -0.49999999999873539862, LOG_L3 = 0.33333399640540911563, LOG_L4 = -0.25000096727866272713;
 
 #ifndef PFR_FAST_MAGIC
-#define PFR_FAST_MAGIC 1   // integer <-> double conversions of log / exp as "magic number" FP64 adds (2^52 + 2^51 shifts the integer
+#define PFR_FAST_MAGIC 3   // bit 0: log, bit 1: exp -- integer <-> double conversions as "magic number" FP64 adds (2^52 + 2^51 shifts the integer
                            // into the low mantissa word) instead of I2F.F64 / F2I.F64 on the XU pipe: one DADD more per call on the
                            // FP64 pipe, three conversions fewer per log + exp pair on the (16 lanes / clk) XU pipe
 #endif
@@ -46,7 +46,7 @@ __device__ __forceinline__ double fast_log(double x, const double2* __restrict__
     double p = fma(r, LOG_L4, LOG_L3);
     p = fma(r, p, LOG_L2);
     p = fma(r * r, p, r);
-#if PFR_FAST_MAGIC
+#if PFR_FAST_MAGIC & 1
     // the biased exponent dropped into the low mantissa word of 2^52 is the double 2^52 + (e + 1023), exactly
     const double ed = __hiloint2double(0x43300000, hi >> 20) - (4503599627370496.0 + 1023.0);
 #else
@@ -69,7 +69,7 @@ __device__ __forceinline__ double exp_finish(double T, double p, int k) {
 }
 
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
-#if PFR_FAST_MAGIC
+#if PFR_FAST_MAGIC & 2
     const double sh = fma(x, EXP_ARG_SCALE, MAGIC_52_51);   // the sum is rounded to an integer (ties to even)
     const int k = __double2loint(sh);
     const double kd = sh - MAGIC_52_51;
@@ -89,9 +89,14 @@ __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ 
 // is taken in d with the powers of ln2 / 256 folded into its coefficients
 __device__ __forceinline__ double fast_exp_scaled(double xs, const double* __restrict__ tab) {
     constexpr double C1 = LN2 / EXPTAB_N, C2 = C1 * C1 / 2.0, C3 = C1 * C1 * C1 / 6.0, C4 = C1 * C1 * C1 * C1 / 24.0;
+#if PFR_FAST_MAGIC & 2
     const double sh = xs + MAGIC_52_51;
     const int k = __double2loint(sh);
     const double d = xs - (sh - MAGIC_52_51);
+#else
+    const int k = __double2int_rn(xs);          // F2I + I2F on the XU pipe: two issue slots instead of the six of three FP64 adds
+    const double d = xs - (double)k;
+#endif
     double p = fma(d, C4, C3);
     p = fma(d, p, C2);
     p = fma(d, p, C1);
